@@ -1,0 +1,129 @@
+/* r2dm_b200 — C ABI of the B200-native R2DM sampling hot path.
+ *
+ * The reference (kazuto1011/r2dm) is pure PyTorch and has no FFI layer; its boundary for this path
+ * is the Python object protocol of models/diffusion/{base,continuous_time,discrete_time}.py and
+ * models/efficient_unet.py.  The entry points below are what a binding for that path calls; the
+ * Python shim in r2dm_b200/ (ctypes) mirrors the reference classes on top of them.  Each function
+ * cites the reference code it replaces (paths relative to the reference repository root).
+ *
+ * Conventions: all pointers are CUDA device pointers owned by the caller (PyTorch) unless marked
+ * "host"; tensors are contiguous fp32 NCHW at the boundary; work is enqueued on `stream`
+ * (a cudaStream_t passed as void*) and never synchronises; every function returns 0 on success or
+ * a negative code, with a message available from r2dm_last_error().  No function allocates device
+ * memory: weights live in a caller-provided arena, activations in a caller-provided workspace.
+ */
+#ifndef R2DM_B200_H
+#define R2DM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct r2dm_model* r2dm_handle;
+
+enum { R2DM_F32 = 0, R2DM_BF16 = 1 }; /* compute/storage type of the U-Net: tf32 or bf16 tensor cores */
+
+/* EfficientUNet constructor arguments (models/efficient_unet.py:194-209, utils/inference.py:38-51). */
+typedef struct {
+  int in_channels;          /* image channels (depth, reflectance) */
+  int height, width;        /* resolution, e.g. 64 x 1024 */
+  int base_channels;
+  int temb_channels;        /* 0 -> 4 * base_channels */
+  int channel_multiplier[4];
+  int num_residual_blocks[4];
+  int gn_num_groups;        /* must be 8 */
+  float gn_eps;
+  int attn_num_heads;
+  int extra_channels;       /* channels of the constant coordinate encoding appended to the input */
+  float residual_scale;     /* ResidualBlock / SelfAttentionBlock `scale` buffer (1/sqrt 2) */
+  int dtype;                /* R2DM_F32 or R2DM_BF16 */
+} r2dm_config;
+
+const char* r2dm_last_error(void);
+int r2dm_version(void);
+
+/* --- lifetime ---------------------------------------------------------------------------------- */
+int r2dm_create(const r2dm_config* cfg, r2dm_handle* out);
+int r2dm_destroy(r2dm_handle h);
+
+/* --- weights: replaces nn.Module.load_state_dict (utils/inference.py:80-81) ------------------------
+ * `name` is the reference state-dict key without the leading "model." (e.g.
+ * "d_block1.residual_blocks.0.conv1.weight"); `src` is the fp32 device tensor.  Convolution and
+ * projection weights are re-packed into the tensor-core operand layout inside the arena.  The
+ * constant coordinate encoding (models/encoding.py) is loaded under the name "coords_encoding.table"
+ * with shape [extra_channels, H, W].  Unknown names return 1 (ignored buffer), not an error. */
+size_t r2dm_weight_arena_bytes(r2dm_handle h);
+int r2dm_bind_weight_arena(r2dm_handle h, void* arena, size_t bytes);
+int r2dm_load_tensor(r2dm_handle h, const char* name, const float* src, const int64_t* shape, int ndim,
+                     void* stream);
+int r2dm_missing_tensors(r2dm_handle h, char* names_out, size_t names_cap); /* returns count */
+
+/* --- workspace for a given batch size ------------------------------------------------------------ */
+size_t r2dm_workspace_bytes(r2dm_handle h, int batch);
+int r2dm_bind_workspace(r2dm_handle h, void* workspace, size_t bytes, int batch, void* stream);
+
+/* --- conditioning: time embedding MLP + all AdaGN projections --------------------------------------
+ * (models/efficient_unet.py:232-237,273-275; models/ops.py:14-29,190-198).  For `rows` network
+ * conditions (log-SNR values or integer steps) writes film[rows][r2dm_film_width()].
+ * scratch: rows * temb_channels floats. */
+int r2dm_film_width(r2dm_handle h);
+int r2dm_cond_embed(r2dm_handle h, const float* cond, int rows, float* scratch, float* film, void* stream);
+
+/* --- EfficientUNet.forward (models/efficient_unet.py:269-295) --------------------------------------
+ * x, pred: [B][in_channels][H][W] fp32.  Sample b uses film row
+ *   (step_ptr ? *step_ptr : 0) * rows_per_step + b * row_batch_stride
+ * so a captured CUDA graph can walk a precomputed per-step table with a device-side counter. */
+int r2dm_unet_forward(r2dm_handle h, const float* x, const float* film, const int* step_ptr,
+                      int rows_per_step, int row_batch_stride, float* pred, void* stream);
+int r2dm_num_launches(r2dm_handle h); /* kernels enqueued by one r2dm_unet_forward */
+
+/* --- sampler step arithmetic (models/diffusion/continuous_time.py:208-229, 296-299;
+ *     discrete_time.py:140-179).  coef rows: {ux, up, kx, k0, kn [, qa, qs]}:
+ *       x0  = clamp(ux*x + up*pred, +-clip)        (clip <= 0 disables)
+ *       x'  = kx*x + k0*x0 + kn*noise
+ *       x'  = mask*(qa*known + qs*noise2) + (1-mask)*x'     when known != NULL (RePaint)
+ * row index as in r2dm_unet_forward. */
+int r2dm_sampler_update(float* x_out, const float* x, const float* pred, const float* noise,
+                        const float* coef, int coef_cols, const int* step_ptr, int rows_per_step,
+                        int row_batch_stride, float clip, const float* known, const float* mask,
+                        const float* noise2, int batch, size_t per_sample, void* stream);
+/* y[b] = ac[b][0]*x[b] + ac[b][1]*noise[b]  (q_step / q_step_from_x_0, continuous_time.py:169-190) */
+int r2dm_axpby(float* y, const float* x, const float* noise, const float* ac, int batch,
+               size_t per_sample, void* stream);
+int r2dm_advance_step(int* step_ptr, int delta, void* stream);
+
+/* --- LiDAR post-processing (sample_and_save.py:52-57, utils/lidar.py:49-70,99-120):
+ * sample [B][2][H][W] in [-1,1] -> out [B][5][H][W] = depth, x, y, z, reflectance.
+ * depth_format: 0 log_depth, 1 inverse_depth, 2 depth.  angles: [2][H][W] (elevation, azimuth). */
+int r2dm_lidar_postprocess(const float* sample, const float* angles, float* out, int batch, int H,
+                           int W, int depth_format, float min_depth, float max_depth, void* stream);
+
+/* --- single-operator entry points (used by the parity tests; same kernels as the network) ----------
+ * All take fp32 NCHW tensors and a scratch buffer for the packed intermediates. */
+size_t r2dm_op_scratch_bytes(int batch, int max_channels, int H, int W);
+/* ops.Conv2d ring 3x3 (taps=9) or 1x1 (taps=1); w OIHW; residual may be NULL; y = (conv+bias+res)*scale */
+int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const float* bias,
+                 const float* residual, float scale, float* y, int B, int Cin, int Cout, int H, int W,
+                 void* scratch, size_t scratch_bytes, void* stream);
+/* GroupNorm(8 groups) [+ FiLM: y = gn(x)*(1+fs)+fb when film_scale != NULL, per sample [B][C]] [+ SiLU] */
+int r2dm_op_groupnorm(int dtype, const float* x, const float* gamma, const float* beta,
+                      const float* film_scale_shift, float eps, int silu, float* y, int B, int C, int H,
+                      int W, void* scratch, size_t scratch_bytes, void* stream);
+/* ops.Resample: dir = +2 (up) or -2 (down) */
+int r2dm_op_resample(int dtype, int dir, const float* x, float* y, int B, int C, int H, int W,
+                     void* scratch, size_t scratch_bytes, void* stream);
+/* attention core on packed qkv [B][3E][H][W] -> [B][E][H][W] */
+int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int heads, int H, int W,
+                      void* scratch, size_t scratch_bytes, void* stream);
+
+/* copy a named intermediate activation of the last forward to fp32 NCHW (debugging / tests);
+ * returns channel count via *C_out etc.  Names: "in_conv", "<block>", "<block>.rb<i>". */
+int r2dm_debug_tensor(r2dm_handle h, const char* name, float* out, int* C, int* H, int* W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2DM_B200_H */

@@ -1,0 +1,117 @@
+"""ctypes binding of libr2dm_b200.so (the C ABI declared in include/r2dm_b200.h).
+
+There is no CPU / PyTorch fallback: if the shared library is missing or fails to load, importing
+the compute path raises.  Build it with `./build.sh` (or `python -c "import __graft_entry__ as g;
+g.build()"`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libr2dm_b200.so")
+
+F32, BF16 = 0, 1
+
+
+class R2dmConfig(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int),
+        ("height", C.c_int),
+        ("width", C.c_int),
+        ("base_channels", C.c_int),
+        ("temb_channels", C.c_int),
+        ("channel_multiplier", C.c_int * 4),
+        ("num_residual_blocks", C.c_int * 4),
+        ("gn_num_groups", C.c_int),
+        ("gn_eps", C.c_float),
+        ("attn_num_heads", C.c_int),
+        ("extra_channels", C.c_int),
+        ("residual_scale", C.c_float),
+        ("dtype", C.c_int),
+    ]
+
+
+class R2dmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_P = C.c_void_p
+_SIGS = {
+    "r2dm_last_error": (C.c_char_p, []),
+    "r2dm_version": (C.c_int, []),
+    "r2dm_create": (C.c_int, [C.POINTER(R2dmConfig), C.POINTER(_P)]),
+    "r2dm_destroy": (C.c_int, [_P]),
+    "r2dm_weight_arena_bytes": (C.c_size_t, [_P]),
+    "r2dm_bind_weight_arena": (C.c_int, [_P, _P, C.c_size_t]),
+    "r2dm_load_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, _P]),
+    "r2dm_missing_tensors": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
+    "r2dm_workspace_bytes": (C.c_size_t, [_P, C.c_int]),
+    "r2dm_bind_workspace": (C.c_int, [_P, _P, C.c_size_t, C.c_int, _P]),
+    "r2dm_film_width": (C.c_int, [_P]),
+    "r2dm_cond_embed": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "r2dm_unet_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "r2dm_num_launches": (C.c_int, [_P]),
+    "r2dm_sampler_update": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_float,
+                                      _P, _P, _P, C.c_int, C.c_size_t, _P]),
+    "r2dm_axpby": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_size_t, _P]),
+    "r2dm_advance_step": (C.c_int, [_P, C.c_int, _P]),
+    "r2dm_lidar_postprocess": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                         C.c_float, _P]),
+    "r2dm_op_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "r2dm_op_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int,
+                               C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "r2dm_op_groupnorm": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "r2dm_op_resample": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P,
+                                   C.c_size_t, _P]),
+    "r2dm_op_attention": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P,
+                                    C.c_size_t, _P]),
+    "r2dm_debug_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), _P]),
+}
+EXPORTS = tuple(_SIGS)
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises R2dmError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise R2dmError(f"{LIB_PATH} not found: the CUDA extension is not built (run ./build.sh); "
+                            "r2dm_b200 has no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> int:
+    if rc < 0:
+        msg = lib().r2dm_last_error().decode()
+        raise R2dmError(f"{what or 'r2dm call'} failed ({rc}): {msg}")
+    return rc
+
+
+def ptr(t) -> int:
+    """Device pointer of a contiguous CUDA tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return t.data_ptr()
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream

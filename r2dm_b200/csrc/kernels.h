@@ -1,0 +1,123 @@
+// Host-side launcher declarations for the hand-written sm_100a kernels (internal header).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace r2dm {
+
+constexpr int kNU = 8;  // GroupNorm statistic units per tensor (= gn_num_groups of the reference)
+
+enum DType : int { kF32 = 0, kBF16 = 1 };
+inline int dtype_size(int dt) { return dt == kBF16 ? 2 : 4; }
+inline int dtype_cw(int dt) { return 16 / dtype_size(dt); }
+
+// A planar-16 activation tensor (see common.cuh) plus its GroupNorm partial statistics.
+struct PT {
+  void* ptr = nullptr;
+  int B = 0, C = 0, H = 0, W = 0;
+  float* stats = nullptr;  // [B][kNU][slots][2] (sum, sum of squares), or null
+  int slots = 0;
+  size_t bytes(int dt) const { return static_cast<size_t>(B) * C * H * (W + 2) * dtype_size(dt); }
+};
+
+// ------------------------------------------------------------------ implicit-GEMM convolution
+struct ConvLaunch {
+  int dtype;          // kF32 (tf32 tensor cores) or kBF16
+  int taps;           // 9 (3x3 ring conv) or 1 (1x1 conv / linear over tokens)
+  int nt, ht;         // N tile (output channels per CTA) and output rows per tile
+  PT in0, in1;        // input(s); in1.ptr == nullptr unless the input is a channel concat
+  int cin_pad;        // total input channels incl. zero padding (multiple of the stage K)
+  const void* wpacked;  // packed weights (pack_conv_weight)
+  const float* bias;  // [cout] fp32 (zero padded to cout_pad)
+  int cout, cout_pad;
+  PT out;             // output tensor (planar-16), unless out_nchw
+  const void* residual;  // planar-16 tensor added before scaling, or null
+  float scale;        // applied after bias (+ residual)
+  float* out_nchw;    // if non-null: write fp32 [B][cout][H][W] instead of `out`
+  CUtensorMap tmap0, tmap1;
+};
+// Fills l.tmap0/tmap1 for the current in0/in1 pointers.  Returns 0 on success.
+int conv_make_tmaps(ConvLaunch& l);
+int conv_stage_channels(int dtype, int taps);  // K per pipeline stage
+size_t conv_packed_weight_bytes(int dtype, int taps, int nt, int cin_pad, int cout_pad);
+int conv_stat_slots(const ConvLaunch& l);
+cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s);
+// w: fp32 [cout][cin][k][k] (OIHW), k*k == taps
+cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin,
+                             int cin_pad, int cout_pad, void* dst, cudaStream_t s);
+
+// ------------------------------------------------------------------ layout conversion
+cudaError_t pack_nchw(int dtype, const float* src, int B, int Csrc, int H, int W, PT dst,
+                      int c_off, cudaStream_t s);
+cudaError_t unpack_nchw(int dtype, PT src, float* dst, int c_off, int Cdst, cudaStream_t s);
+// x [B][Cx][H][W] fp32 and constant enc [Ce][H][W] fp32 -> planes [plane_begin, plane_end) of dst
+cudaError_t pack_input(int dtype, const float* x, int Cx, const float* enc, int Ce, PT dst,
+                       int plane_begin, int plane_end, cudaStream_t s);
+
+// ------------------------------------------------------------------ GroupNorm / AdaGN (+SiLU)
+struct GnApply {
+  int dtype;
+  PT src0, src1;      // channel concat [src0, src1] (src1.ptr null if single)
+  PT dst;
+  int groups;
+  float eps;
+  const float* gamma; const float* beta;  // affine GN, or null for AdaGN
+  const float* film;  // AdaGN: table [rows][film_stride]; scale at film_off, shift at +C
+  int film_stride, film_off;
+  const int* step_ptr;  // device int: current table row base (null -> 0)
+  int row_batch_stride; // row = step * rows_per_step + b * row_batch_stride
+  int rows_per_step;
+  int silu;
+};
+cudaError_t gn_apply_launch(const GnApply& g, cudaStream_t s);
+// statistics of a tensor that was not produced by a stats-emitting kernel (tests / external input)
+cudaError_t tensor_stats_launch(int dtype, PT t, cudaStream_t s);
+int tensor_stats_slots(int dtype, const PT& t);
+
+// ------------------------------------------------------------------ FIR resampling
+cudaError_t down2_launch(int dtype, PT src, PT dst, cudaStream_t s);  // dst gets stats
+int down2_stat_slots(int dtype, const PT& dst);
+cudaError_t up2_launch(int dtype, PT src, PT dst, cudaStream_t s);
+
+// ------------------------------------------------------------------ attention core
+// qkv: planar-16 tensor with 3E channels ([q;k;v]); out: E channels. softmax(q k^T / sqrt(hd)) v
+cudaError_t attention_launch(int dtype, PT qkv, PT out, int heads, cudaStream_t s);
+
+// ------------------------------------------------------------------ conditioning table
+struct CondEmbed {
+  const float* cond; int rows;        // [rows] network conditions (log-SNR or integer step)
+  int base_ch, temb_ch;               // sinusoid width, MLP width
+  const float* w1; const float* b1;   // [temb][base], [temb]
+  const float* w2; const float* b2;   // [temb][temb], [temb]
+  const float* wf; const float* bf;   // all AdaGN projections stacked: [F][temb], [F]
+  int F;
+  float* temb_scratch;                // [rows][temb]
+  float* film;                        // [rows][F]
+};
+cudaError_t cond_embed_launch(const CondEmbed& c, cudaStream_t s);
+
+// ------------------------------------------------------------------ sampler elementwise
+// x0 = clamp(ux*x + up*pred); x' = kx*x + k0*x0 + kn*noise ; coef rows of 5 floats, row index =
+// step*rows_per_step + b*row_batch_stride.  Optional RePaint blend with the re-noised known image:
+// x' = mask*(qa*known + qs*noise2) + (1-mask)*x'   (coef row has 7 floats then).
+struct SamplerUpdate {
+  float* x; const float* pred; const float* noise;
+  const float* coef; int coef_cols;
+  const int* step_ptr; int rows_per_step, row_batch_stride;
+  float clip;          // <= 0: no clipping
+  const float* known; const float* mask; const float* noise2;  // RePaint (or null)
+  float* x_out;        // may alias x
+  int B; size_t per_sample;
+};
+cudaError_t sampler_update_launch(const SamplerUpdate& u, cudaStream_t s);
+// y = a[b]*x + c[b]*noise  (q_step / q_step_from_x_0), coefficients on device: ac[b][2]
+cudaError_t axpby_launch(const float* x, const float* noise, const float* ac, float* y, int B,
+                         size_t per_sample, cudaStream_t s);
+cudaError_t advance_step_launch(int* step_ptr, int delta, cudaStream_t s);
+// [depth, x, y, z, reflectance] from a sample in [-1, 1] (sample_and_save.py:52-57)
+cudaError_t lidar_postprocess_launch(const float* sample, const float* angles, float* out, int B,
+                                     int H, int W, int depth_format, float min_depth,
+                                     float max_depth, cudaStream_t s);
+
+}  // namespace r2dm

@@ -1,0 +1,808 @@
+// Host runtime + C ABI: weight arena, workspace planning and the per-forward launch program of the
+// EfficientUNet (models/efficient_unet.py:188-295) built from the kernels in this directory.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/r2dm_b200.h"
+#include "kernels.h"
+
+using namespace r2dm;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) return fail(-2, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+struct ConvW {
+  std::string name;
+  int taps = 9, cin = 0, cout = 0, cin_pad = 0, cout_pad = 0, nt = 64;
+  size_t w_off = 0, b_off = 0;
+  bool w_ok = false, b_ok = false;
+};
+struct RawW {  // fp32 tensor copied verbatim into the arena at dst_off (+ row offset for stacked)
+  std::string name;
+  size_t off = 0, numel = 0;
+  bool ok = false;
+};
+
+struct BlockSpec {
+  std::string name;
+  int cin, cout, nres, down, up, attn;
+};
+
+// A planned activation tensor.
+struct TRef { int id = -1; };
+
+struct Op {
+  enum Kind { PACK_INPUT, CONV, GN, DOWN, UP, ATTN } kind;
+  ConvLaunch conv;
+  GnApply gn;
+  PT a, b;
+  int heads = 0;
+  int conv_w = -1;        // index into convs (weights/bias resolved at bind)
+  int gn_gamma = -1;      // raw index of gamma (beta = +1), or -1 for AdaGN
+  bool is_output = false; // network output conv (writes pred NCHW)
+};
+
+}  // namespace
+
+struct r2dm_model {
+  r2dm_config cfg;
+  int dtype, cw, T, F = 0;
+  int C[5];
+  std::vector<BlockSpec> blocks;
+  std::vector<ConvW> convs;
+  std::vector<RawW> raws;
+  std::map<std::string, int> conv_by_name, raw_by_name;
+  std::map<std::string, std::pair<int, int>> film_rows;  // proj name -> (row offset, rows)
+  size_t arena_bytes = 0;
+  uint8_t* arena = nullptr;
+  int raw_w1, raw_b1, raw_w2, raw_b2, raw_wf, raw_bf, raw_enc;
+  int cin0_pad;
+  bool keep_all = false;
+
+  // workspace / program
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  int batch = 0;
+  std::vector<Op> prog;
+  std::map<std::string, PT> named;
+  int n_launches = 0;
+
+  float* raw_ptr(int i) const { return reinterpret_cast<float*>(arena + raws[i].off); }
+};
+
+namespace {
+
+int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
+  RawW r;
+  r.name = name;
+  r.numel = numel;
+  r.off = m->arena_bytes;
+  m->arena_bytes += align_up(numel * sizeof(float), 256);
+  m->raws.push_back(r);
+  m->raw_by_name[name] = static_cast<int>(m->raws.size()) - 1;
+  return static_cast<int>(m->raws.size()) - 1;
+}
+
+int pick_nt(int taps, int cout) {
+  (void)taps;
+  if (cout <= 16) return 16;
+  return cout % 128 == 0 ? 128 : 64;
+}
+
+int add_conv(r2dm_model* m, const std::string& name, int taps, int cin, int cout) {
+  ConvW c;
+  c.name = name;
+  c.taps = taps; c.cin = cin; c.cout = cout;
+  c.nt = pick_nt(taps, cout);
+  c.cin_pad = round_up(cin, conv_stage_channels(m->dtype, taps));
+  c.cout_pad = round_up(cout, c.nt);
+  c.w_off = m->arena_bytes;
+  m->arena_bytes += align_up(conv_packed_weight_bytes(m->dtype, taps, c.nt, c.cin_pad, c.cout_pad), 256);
+  c.b_off = m->arena_bytes;
+  m->arena_bytes += align_up(static_cast<size_t>(c.cout_pad) * sizeof(float), 256);
+  m->convs.push_back(c);
+  m->conv_by_name[name] = static_cast<int>(m->convs.size()) - 1;
+  return static_cast<int>(m->convs.size()) - 1;
+}
+
+// Mirrors the module tree of EfficientUNet.__init__ (efficient_unet.py:212-267).
+int plan_weights(r2dm_model* m) {
+  const r2dm_config& c = m->cfg;
+  m->C[0] = c.base_channels;
+  for (int i = 0; i < 4; ++i) m->C[i + 1] = c.base_channels * c.channel_multiplier[i];
+  const int* C = m->C;
+  const int* N = c.num_residual_blocks;
+  m->blocks = {
+      {"d_block1", C[0], C[1], N[0], 1, 1, 0}, {"d_block2", C[1], C[2], N[1], 2, 1, 0},
+      {"d_block3", C[2], C[3], N[2], 2, 1, 0}, {"d_block4", C[3], C[4], N[3], 2, 1, 1},
+      {"u_block4", C[4], C[3], N[3], 1, 2, 1}, {"u_block3", C[3] + C[3], C[2], N[2], 1, 2, 0},
+      {"u_block2", C[2] + C[2], C[1], N[1], 1, 2, 0}, {"u_block1", C[1] + C[1], C[0], N[0], 1, 1, 0},
+  };
+  const int T = m->T;
+  m->raw_w1 = add_raw(m, "time_embedding.1.weight", static_cast<size_t>(T) * c.base_channels);
+  m->raw_b1 = add_raw(m, "time_embedding.1.bias", T);
+  m->raw_w2 = add_raw(m, "time_embedding.3.weight", static_cast<size_t>(T) * T);
+  m->raw_b2 = add_raw(m, "time_embedding.3.bias", T);
+  m->raw_enc = c.extra_channels > 0
+                   ? add_raw(m, "coords_encoding.table", static_cast<size_t>(c.extra_channels) * c.height * c.width)
+                   : -1;
+  add_conv(m, "in_conv", 9, c.in_channels + c.extra_channels, C[0]);
+  int F = 0;
+  for (const BlockSpec& b : m->blocks) {
+    if (b.down > 1) add_conv(m, b.name + ".downsample.0", 9, b.cin, b.cout);
+    for (int i = 0; i < b.nres; ++i) {
+      const int ci = (i != 0 || b.down > 1) ? b.cout : b.cin;
+      const std::string p = b.name + ".residual_blocks." + std::to_string(i);
+      add_raw(m, p + ".norm1.weight", ci);
+      add_raw(m, p + ".norm1.bias", ci);
+      add_conv(m, p + ".conv1", 9, ci, b.cout);
+      m->film_rows[p + ".norm2.proj.1"] = {F, 2 * b.cout};
+      F += 2 * b.cout;
+      add_conv(m, p + ".conv2", 9, b.cout, b.cout);
+      if (ci != b.cout) add_conv(m, p + ".skip", 1, ci, b.cout);
+    }
+    if (b.attn) {
+      const std::string p = b.name + ".self_attn_block";
+      add_raw(m, p + ".norm.weight", b.cout);
+      add_raw(m, p + ".norm.bias", b.cout);
+      add_conv(m, p + ".attn.in_proj", 1, b.cout, 3 * b.cout);
+      add_conv(m, p + ".attn.out_proj", 1, b.cout, b.cout);
+    }
+    if (b.up > 1) add_conv(m, b.name + ".upsample.1", 9, b.cout, b.cout);
+  }
+  add_conv(m, "out_conv", 9, C[0], c.in_channels);
+  m->F = F;
+  m->raw_wf = add_raw(m, "__film_weight", static_cast<size_t>(F) * T);
+  m->raw_bf = add_raw(m, "__film_bias", F);
+  m->raws[m->raw_wf].ok = m->raws[m->raw_bf].ok = true;  // filled piecewise via film_rows
+  m->cin0_pad = m->convs[m->conv_by_name["in_conv"]].cin_pad;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ workspace planner
+struct Planner {
+  r2dm_model* m;
+  uint8_t* base;       // nullptr for the dry run
+  size_t top = 0;
+  int B;
+  struct Buf { size_t off, bytes; int refs; };
+  std::vector<Buf> bufs;
+  std::multimap<size_t, size_t> free_list;  // bytes -> offset
+  std::vector<PT> tensors;
+  std::vector<int> tensor_buf;
+
+  size_t alloc(size_t bytes) {
+    bytes = align_up(bytes, 1024);
+    if (!m->keep_all) {
+      auto it = free_list.find(bytes);
+      if (it != free_list.end()) {
+        size_t off = it->second;
+        free_list.erase(it);
+        return off;
+      }
+    }
+    size_t off = top;
+    top += bytes;
+    return off;
+  }
+  int new_tensor(int C, int H, int W, int slots) {
+    PT t;
+    t.B = B; t.C = C; t.H = H; t.W = W; t.slots = slots;
+    const size_t data = align_up(t.bytes(m->dtype), 256);
+    const size_t st = slots > 0 ? static_cast<size_t>(B) * kNU * slots * 2 * sizeof(float) : 0;
+    const size_t bytes = align_up(data + st, 1024);
+    const size_t off = alloc(bytes);
+    bufs.push_back({off, bytes, 1});
+    t.ptr = base ? base + off : reinterpret_cast<void*>(off + 4096);  // dry run: fake non-null
+    t.stats = slots > 0 ? reinterpret_cast<float*>(static_cast<uint8_t*>(t.ptr) + data) : nullptr;
+    tensors.push_back(t);
+    tensor_buf.push_back(static_cast<int>(bufs.size()) - 1);
+    return static_cast<int>(tensors.size()) - 1;
+  }
+  void retain(int id) { bufs[tensor_buf[id]].refs++; }
+  void release(int id) {
+    Buf& b = bufs[tensor_buf[id]];
+    if (--b.refs == 0) free_list.insert({b.bytes, b.off});
+  }
+};
+
+struct Builder {
+  r2dm_model* m;
+  Planner pl;
+  std::vector<Op> prog;
+  std::map<std::string, PT> named;
+
+  const PT& T(int id) const { return pl.tensors[id]; }
+
+  int conv(const std::string& wname, int in0, int in1, int residual, float scale, bool want_stats,
+           bool is_output = false) {
+    const int wi = m->conv_by_name.at(wname);
+    const ConvW& w = m->convs[wi];
+    const PT& a = T(in0);
+    Op op;
+    op.kind = Op::CONV;
+    op.conv_w = wi;
+    op.is_output = is_output;
+    ConvLaunch& l = op.conv;
+    memset(&l, 0, sizeof(l));
+    l.dtype = m->dtype; l.taps = w.taps; l.nt = w.nt;
+    if (w.taps == 9) l.ht = (w.nt == 128) ? (a.H >= 2 ? 2 : 1) : (a.H % 4 == 0 ? 4 : (a.H >= 2 ? 2 : 1));
+    else l.ht = a.H >= 2 ? 2 : 1;
+    if (w.nt == 16 && l.ht != 4) l.ht = 4;
+    l.in0 = a;
+    if (in1 >= 0) l.in1 = T(in1);
+    l.cin_pad = w.cin_pad; l.cout = w.cout; l.cout_pad = w.cout_pad;
+    l.scale = scale;
+    int out_id = -1;
+    if (!is_output) {
+      int slots = 0;
+      if (want_stats) slots = ((a.H + l.ht - 1) / l.ht) * (a.W / 128);
+      out_id = pl.new_tensor(w.cout_pad, a.H, a.W, slots);
+      l.out = T(out_id);
+    } else {
+      l.out = a;  // geometry only
+      l.out.C = w.cout_pad;
+      l.out.stats = nullptr; l.out.slots = 0;
+    }
+    l.residual = residual >= 0 ? T(residual).ptr : nullptr;
+    prog.push_back(op);
+    return out_id;
+  }
+  int gn(int src0, int src1, int gamma_raw, const std::string& film_name, bool silu) {
+    const PT& a = T(src0);
+    const int Ctot = a.C + (src1 >= 0 ? T(src1).C : 0);
+    const int out = pl.new_tensor(Ctot, a.H, a.W, 0);
+    Op op;
+    op.kind = Op::GN;
+    GnApply& g = op.gn;
+    memset(&g, 0, sizeof(g));
+    g.dtype = m->dtype;
+    g.src0 = T(src0);
+    if (src1 >= 0) g.src1 = T(src1);
+    g.dst = T(out);
+    g.groups = m->cfg.gn_num_groups; g.eps = m->cfg.gn_eps;
+    g.silu = silu ? 1 : 0;
+    op.gn_gamma = gamma_raw;
+    if (gamma_raw < 0) {
+      g.film_off = m->film_rows.at(film_name).first;
+      g.film_stride = m->F;
+    }
+    prog.push_back(op);
+    return out;
+  }
+  int resample(int src, int dir) {
+    const PT& a = T(src);
+    Op op;
+    int out;
+    if (dir < 0) {
+      PT tmp; tmp.B = a.B; tmp.C = a.C; tmp.H = a.H / 2; tmp.W = a.W / 2;
+      out = pl.new_tensor(a.C, a.H / 2, a.W / 2, down2_stat_slots(m->dtype, tmp));
+      op.kind = Op::DOWN;
+    } else {
+      out = pl.new_tensor(a.C, a.H * 2, a.W * 2, 0);
+      op.kind = Op::UP;
+    }
+    op.a = T(src); op.b = T(out);
+    prog.push_back(op);
+    return out;
+  }
+
+  int build() {
+    const r2dm_config& c = m->cfg;
+    const float rs = c.residual_scale;
+    // input staging tensor: [x | coords encoding | 0]
+    const int xin = pl.new_tensor(m->cin0_pad, c.height, c.width, 0);
+    named["__input"] = T(xin);
+    {
+      Op op; op.kind = Op::PACK_INPUT; op.a = T(xin);
+      prog.push_back(op);
+    }
+    int h = conv("in_conv", xin, -1, -1, 1.f, true);
+    named["in_conv"] = T(h);
+    std::vector<int> skips;
+    for (const BlockSpec& b : m->blocks) {
+      int h2 = -1;  // second half of a concat input
+      if (b.name[0] == 'u' && b.name != "u_block4") { h2 = skips.back(); skips.pop_back(); }
+      if (b.down > 1) {
+        const int t = conv(b.name + ".downsample.0", h, -1, -1, 1.f, false);
+        pl.release(h);
+        h = resample(t, -2);
+        pl.release(t);
+      }
+      for (int i = 0; i < b.nres; ++i) {
+        const std::string p = b.name + ".residual_blocks." + std::to_string(i);
+        const int x0 = h, x1 = (i == 0) ? h2 : -1;
+        const int xn = gn(x0, x1, m->raw_by_name.at(p + ".norm1.weight"), "", true);
+        const int h1 = conv(p + ".conv1", xn, -1, -1, 1.f, true);
+        pl.release(xn);
+        const int hn = gn(h1, -1, -1, p + ".norm2.proj.1", true);
+        pl.release(h1);
+        int res = x0, sk = -1;
+        if (m->conv_by_name.count(p + ".skip")) {
+          sk = conv(p + ".skip", x0, x1, -1, 1.f, false);
+          res = sk;
+        }
+        const int o = conv(p + ".conv2", hn, -1, res, rs, true);
+        pl.release(hn);
+        if (sk >= 0) pl.release(sk);
+        pl.release(x0);
+        if (x1 >= 0) pl.release(x1);
+        h = o;
+        named[b.name + ".rb" + std::to_string(i)] = T(h);
+      }
+      if (b.attn) {
+        const std::string p = b.name + ".self_attn_block";
+        const int xn = gn(h, -1, m->raw_by_name.at(p + ".norm.weight"), "", false);
+        const int qkv = conv(p + ".attn.in_proj", xn, -1, -1, 1.f, false);
+        pl.release(xn);
+        const int att = pl.new_tensor(b.cout, T(h).H, T(h).W, 0);
+        {
+          Op op; op.kind = Op::ATTN; op.a = T(qkv); op.b = T(att); op.heads = c.attn_num_heads;
+          prog.push_back(op);
+        }
+        pl.release(qkv);
+        const int o = conv(p + ".attn.out_proj", att, -1, h, rs, true);
+        pl.release(att);
+        pl.release(h);
+        h = o;
+      }
+      if (b.up > 1) {
+        const int t = resample(h, +2);
+        pl.release(h);
+        h = conv(b.name + ".upsample.1", t, -1, -1, 1.f, true);
+        pl.release(t);
+      }
+      named[b.name] = T(h);
+      if (b.name == "d_block1" || b.name == "d_block2" || b.name == "d_block3") {
+        skips.push_back(h);
+        pl.retain(h);
+      }
+    }
+    conv("out_conv", h, -1, -1, 1.f, false, true);
+    pl.release(h);
+    return 0;
+  }
+};
+
+int validate_config(const r2dm_config& c) {
+  if (c.gn_num_groups != kNU) return fail(-1, "gn_num_groups must be %d", kNU);
+  if (c.base_channels % 64 != 0) return fail(-1, "base_channels must be a multiple of 64");
+  if (c.width % 1024 != 0) return fail(-1, "width must be a multiple of 1024 (bottleneck rows of >=128 px)");
+  if (c.height % 8 != 0 || c.height < 8) return fail(-1, "height must be a multiple of 8");
+  if (c.dtype != R2DM_F32 && c.dtype != R2DM_BF16) return fail(-1, "dtype must be R2DM_F32 or R2DM_BF16");
+  for (int i = 0; i < 4; ++i) {
+    if (c.channel_multiplier[i] < 1 || c.num_residual_blocks[i] < 1) return fail(-1, "bad multiplier / block count");
+  }
+  const int E4 = c.base_channels * c.channel_multiplier[3], E3 = c.base_channels * c.channel_multiplier[2];
+  for (int E : {E4, E3}) {
+    if (E % c.attn_num_heads) return fail(-1, "attention width %d not divisible by heads", E);
+    const int hd = E / c.attn_num_heads;
+    if (hd != 32 && hd != 64) return fail(-1, "head dim %d unsupported (32 or 64)", hd);
+  }
+  if (c.in_channels < 1 || c.in_channels > 16) return fail(-1, "in_channels out of range");
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+extern "C" {
+
+const char* r2dm_last_error(void) { return g_err; }
+int r2dm_version(void) { return 100; }
+
+int r2dm_create(const r2dm_config* cfg, r2dm_handle* out) {
+  if (!cfg || !out) return fail(-1, "null argument");
+  int rc = validate_config(*cfg);
+  if (rc) return rc;
+  r2dm_model* m = new r2dm_model();
+  m->cfg = *cfg;
+  if (m->cfg.temb_channels <= 0) m->cfg.temb_channels = 4 * cfg->base_channels;
+  if (m->cfg.residual_scale <= 0.f) m->cfg.residual_scale = 0.70710678118654752f;
+  m->dtype = cfg->dtype;
+  m->cw = dtype_cw(m->dtype);
+  m->T = m->cfg.temb_channels;
+  plan_weights(m);
+  const char* dbg = getenv("R2DM_KEEP_ACTIVATIONS");
+  m->keep_all = dbg && dbg[0] == '1';
+  *out = m;
+  return 0;
+}
+
+int r2dm_destroy(r2dm_handle h) {
+  delete h;
+  return 0;
+}
+
+size_t r2dm_weight_arena_bytes(r2dm_handle h) { return h ? h->arena_bytes : 0; }
+
+int r2dm_bind_weight_arena(r2dm_handle h, void* arena, size_t bytes) {
+  if (!h || !arena) return fail(-1, "null argument");
+  if (bytes < h->arena_bytes) return fail(-1, "weight arena too small: %zu < %zu", bytes, h->arena_bytes);
+  if (reinterpret_cast<uintptr_t>(arena) % 256) return fail(-1, "weight arena must be 256-byte aligned");
+  h->arena = static_cast<uint8_t*>(arena);
+  return 0;
+}
+
+static size_t numel_of(const int64_t* shape, int ndim) {
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= static_cast<size_t>(shape[i]);
+  return n;
+}
+
+int r2dm_load_tensor(r2dm_handle h, const char* name_c, const float* src, const int64_t* shape, int ndim,
+                     void* stream) {
+  if (!h || !name_c || !src) return fail(-1, "null argument");
+  if (!h->arena) return fail(-1, "bind the weight arena first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::string name(name_c);
+  const size_t n = numel_of(shape, ndim);
+  // attention projections are stored as 1x1 convolutions
+  auto ends_with = [&](const char* suf) {
+    const size_t l = strlen(suf);
+    return name.size() >= l && name.compare(name.size() - l, l, suf) == 0;
+  };
+  std::string cname;
+  bool is_w = false, is_b = false;
+  if (ends_with(".attn.in_proj_weight")) { cname = name.substr(0, name.size() - 7); is_w = true; }
+  else if (ends_with(".attn.in_proj_bias")) { cname = name.substr(0, name.size() - 5); is_b = true; }
+  else if (ends_with(".weight")) { cname = name.substr(0, name.size() - 7); is_w = true; }
+  else if (ends_with(".bias")) { cname = name.substr(0, name.size() - 5); is_b = true; }
+  auto ci = h->conv_by_name.find(cname);
+  if ((is_w || is_b) && ci != h->conv_by_name.end()) {
+    ConvW& c = h->convs[ci->second];
+    if (is_w) {
+      if (n != static_cast<size_t>(c.cout) * c.cin * c.taps)
+        return fail(-3, "%s: expected %d x %d x %d elements, got %zu", name_c, c.cout, c.cin, c.taps, n);
+      CUDA_TRY(pack_conv_weight(h->dtype, c.taps, c.nt, src, c.cout, c.cin, c.cin_pad, c.cout_pad,
+                                h->arena + c.w_off, s));
+      c.w_ok = true;
+    } else {
+      if (n != static_cast<size_t>(c.cout)) return fail(-3, "%s: expected %d elements, got %zu", name_c, c.cout, n);
+      CUDA_TRY(cudaMemsetAsync(h->arena + c.b_off, 0, static_cast<size_t>(c.cout_pad) * sizeof(float), s));
+      CUDA_TRY(cudaMemcpyAsync(h->arena + c.b_off, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      c.b_ok = true;
+    }
+    return 0;
+  }
+  auto fi = h->film_rows.find(cname);
+  if ((is_w || is_b) && fi != h->film_rows.end()) {
+    const int row0 = fi->second.first, rows = fi->second.second;
+    if (is_w) {
+      if (n != static_cast<size_t>(rows) * h->T) return fail(-3, "%s: bad shape", name_c);
+      CUDA_TRY(cudaMemcpyAsync(h->raw_ptr(h->raw_wf) + static_cast<size_t>(row0) * h->T, src, n * sizeof(float),
+                               cudaMemcpyDeviceToDevice, s));
+    } else {
+      if (n != static_cast<size_t>(rows)) return fail(-3, "%s: bad shape", name_c);
+      CUDA_TRY(cudaMemcpyAsync(h->raw_ptr(h->raw_bf) + row0, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    // bookkeeping: mark via a pseudo raw entry
+    h->raw_by_name.emplace(name, -1);
+    return 0;
+  }
+  auto ri = h->raw_by_name.find(name);
+  if (ri != h->raw_by_name.end() && ri->second >= 0) {
+    RawW& r = h->raws[ri->second];
+    if (n != r.numel) return fail(-3, "%s: expected %zu elements, got %zu", name_c, r.numel, n);
+    CUDA_TRY(cudaMemcpyAsync(h->arena + r.off, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    r.ok = true;
+    return 0;
+  }
+  return 1;  // not a tensor this path consumes (buffers such as coords, scale, kernel, _dummy)
+}
+
+int r2dm_missing_tensors(r2dm_handle h, char* names_out, size_t cap) {
+  if (!h) return fail(-1, "null argument");
+  std::string acc;
+  int n = 0;
+  auto add = [&](const std::string& s) { ++n; acc += s; acc += '\n'; };
+  for (const ConvW& c : h->convs) {
+    if (!c.w_ok) add(c.name + ".weight");
+    if (!c.b_ok) add(c.name + ".bias");
+  }
+  for (const RawW& r : h->raws)
+    if (!r.ok) add(r.name);
+  for (const auto& kv : h->film_rows) {
+    if (!h->raw_by_name.count(kv.first + ".weight")) add(kv.first + ".weight");
+    if (!h->raw_by_name.count(kv.first + ".bias")) add(kv.first + ".bias");
+  }
+  if (names_out && cap > 0) {
+    strncpy(names_out, acc.c_str(), cap - 1);
+    names_out[cap - 1] = 0;
+  }
+  return n;
+}
+
+size_t r2dm_workspace_bytes(r2dm_handle h, int batch) {
+  if (!h || batch < 1) return 0;
+  Builder b;
+  b.m = h;
+  b.pl.m = h; b.pl.base = nullptr; b.pl.B = batch;
+  b.build();
+  return b.pl.top + 4096;
+}
+
+int r2dm_bind_workspace(r2dm_handle h, void* workspace, size_t bytes, int batch, void* stream) {
+  if (!h || !workspace || batch < 1) return fail(-1, "bad argument");
+  if (!h->arena) return fail(-1, "bind the weight arena first");
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(-1, "workspace must be 1024-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Builder b;
+  b.m = h;
+  b.pl.m = h; b.pl.base = static_cast<uint8_t*>(workspace); b.pl.B = batch;
+  b.build();
+  if (b.pl.top > bytes) return fail(-1, "workspace too small: %zu < %zu", bytes, b.pl.top);
+  h->ws = static_cast<uint8_t*>(workspace);
+  h->ws_bytes = bytes;
+  h->batch = batch;
+  h->prog = b.prog;
+  h->named = b.named;
+  // resolve weights, build tensor maps
+  int launches = 0;
+  for (Op& op : h->prog) {
+    if (op.kind == Op::CONV) {
+      const ConvW& w = h->convs[op.conv_w];
+      op.conv.wpacked = h->arena + w.w_off;
+      op.conv.bias = reinterpret_cast<const float*>(h->arena + w.b_off);
+      int rc = conv_make_tmaps(op.conv);
+      if (rc) return fail(-4, "cuTensorMapEncodeTiled failed for %s (%d)", w.name.c_str(), rc);
+    } else if (op.kind == Op::GN && op.gn_gamma >= 0) {
+      op.gn.gamma = h->raw_ptr(op.gn_gamma);
+      op.gn.beta = h->raw_ptr(op.gn_gamma + 1);
+    }
+    ++launches;
+  }
+  h->n_launches = launches;
+  // constant planes of the input staging tensor (coordinate encoding + zero padding)
+  const PT& xin = h->named.at("__input");
+  CUDA_TRY(cudaMemsetAsync(xin.ptr, 0, xin.bytes(h->dtype), s));
+  // all planes once (x = null -> image channels read as 0); forwards rewrite only the image planes
+  CUDA_TRY(pack_input(h->dtype, nullptr, h->cfg.in_channels, h->raw_enc >= 0 ? h->raw_ptr(h->raw_enc) : nullptr,
+                      h->cfg.extra_channels, xin, 0, xin.C / h->cw, s));
+  return 0;
+}
+
+int r2dm_film_width(r2dm_handle h) { return h ? h->F : 0; }
+int r2dm_num_launches(r2dm_handle h) { return h ? h->n_launches : 0; }
+
+int r2dm_cond_embed(r2dm_handle h, const float* cond, int rows, float* scratch, float* film, void* stream) {
+  if (!h || !cond || !scratch || !film || rows < 1) return fail(-1, "bad argument");
+  if (!h->arena) return fail(-1, "bind the weight arena first");
+  CondEmbed c;
+  c.cond = cond; c.rows = rows;
+  c.base_ch = h->cfg.base_channels; c.temb_ch = h->T;
+  c.w1 = h->raw_ptr(h->raw_w1); c.b1 = h->raw_ptr(h->raw_b1);
+  c.w2 = h->raw_ptr(h->raw_w2); c.b2 = h->raw_ptr(h->raw_b2);
+  c.wf = h->raw_ptr(h->raw_wf); c.bf = h->raw_ptr(h->raw_bf);
+  c.F = h->F;
+  c.temb_scratch = scratch; c.film = film;
+  CUDA_TRY(cond_embed_launch(c, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_unet_forward(r2dm_handle h, const float* x, const float* film, const int* step_ptr, int rows_per_step,
+                      int row_batch_stride, float* pred, void* stream) {
+  if (!h || !x || !film || !pred) return fail(-1, "null argument");
+  if (!h->ws) return fail(-1, "bind a workspace first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const r2dm_config& c = h->cfg;
+  for (Op& op : h->prog) {
+    switch (op.kind) {
+      case Op::PACK_INPUT: {
+        // rewrite only the planes that contain image channels; the rest is constant
+        const int pe = (c.in_channels + h->cw - 1) / h->cw;
+        CUDA_TRY(pack_input(h->dtype, x, c.in_channels, h->raw_enc >= 0 ? h->raw_ptr(h->raw_enc) : nullptr,
+                            c.extra_channels, op.a, 0, pe, s));
+        break;
+      }
+      case Op::CONV: {
+        if (op.is_output) op.conv.out_nchw = pred;
+        CUDA_TRY(conv_launch(op.conv, s));
+        break;
+      }
+      case Op::GN: {
+        if (op.gn_gamma < 0) {
+          op.gn.film = film; op.gn.step_ptr = step_ptr;
+          op.gn.rows_per_step = rows_per_step; op.gn.row_batch_stride = row_batch_stride;
+        }
+        CUDA_TRY(gn_apply_launch(op.gn, s));
+        break;
+      }
+      case Op::DOWN: CUDA_TRY(down2_launch(h->dtype, op.a, op.b, s)); break;
+      case Op::UP: CUDA_TRY(up2_launch(h->dtype, op.a, op.b, s)); break;
+      case Op::ATTN: CUDA_TRY(attention_launch(h->dtype, op.a, op.b, op.heads, s)); break;
+    }
+  }
+  return 0;
+}
+
+int r2dm_sampler_update(float* x_out, const float* x, const float* pred, const float* noise, const float* coef,
+                        int coef_cols, const int* step_ptr, int rows_per_step, int row_batch_stride, float clip,
+                        const float* known, const float* mask, const float* noise2, int batch, size_t per_sample,
+                        void* stream) {
+  if (!x_out || !x || !pred || !noise || !coef) return fail(-1, "null argument");
+  if (coef_cols < (known ? 7 : 5)) return fail(-1, "coef_cols too small");
+  if (known && (!mask || !noise2)) return fail(-1, "RePaint blend needs mask and noise2");
+  SamplerUpdate u;
+  u.x = const_cast<float*>(x); u.pred = pred; u.noise = noise; u.coef = coef; u.coef_cols = coef_cols;
+  u.step_ptr = step_ptr; u.rows_per_step = rows_per_step; u.row_batch_stride = row_batch_stride;
+  u.clip = clip; u.known = known; u.mask = mask; u.noise2 = noise2; u.x_out = x_out;
+  u.B = batch; u.per_sample = per_sample;
+  CUDA_TRY(sampler_update_launch(u, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_axpby(float* y, const float* x, const float* noise, const float* ac, int batch, size_t per_sample,
+               void* stream) {
+  if (!y || !x || !noise || !ac) return fail(-1, "null argument");
+  CUDA_TRY(axpby_launch(x, noise, ac, y, batch, per_sample, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_advance_step(int* step_ptr, int delta, void* stream) {
+  if (!step_ptr) return fail(-1, "null argument");
+  CUDA_TRY(advance_step_launch(step_ptr, delta, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_lidar_postprocess(const float* sample, const float* angles, float* out, int batch, int H, int W,
+                           int depth_format, float min_depth, float max_depth, void* stream) {
+  if (!sample || !angles || !out) return fail(-1, "null argument");
+  if (depth_format < 0 || depth_format > 2) return fail(-1, "bad depth_format");
+  CUDA_TRY(lidar_postprocess_launch(sample, angles, out, batch, H, W, depth_format, min_depth, max_depth,
+                                    static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- op hooks
+namespace {
+struct Scratch {
+  uint8_t* base; size_t cap; size_t top = 0;
+  void* take(size_t bytes) {
+    bytes = align_up(bytes, 1024);
+    if (top + bytes > cap) return nullptr;
+    void* p = base + top;
+    top += bytes;
+    return p;
+  }
+};
+PT make_pt(Scratch& sc, int dt, int B, int C, int H, int W, int slots) {
+  PT t; t.B = B; t.C = C; t.H = H; t.W = W; t.slots = slots;
+  t.ptr = sc.take(t.bytes(dt));
+  t.stats = slots > 0 ? static_cast<float*>(sc.take(static_cast<size_t>(B) * kNU * slots * 2 * sizeof(float))) : nullptr;
+  return t;
+}
+}  // namespace
+
+size_t r2dm_op_scratch_bytes(int batch, int max_channels, int H, int W) {
+  const size_t t = static_cast<size_t>(batch) * round_up(max_channels, 64) * H * (W + 2) * 4 + 8192;
+  return 4 * t + (static_cast<size_t>(9) * round_up(max_channels, 64) * round_up(max_channels, 128) * 4) + (1 << 20);
+}
+
+int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const float* bias, const float* residual,
+                 float scale, float* y, int B, int Cin, int Cout, int H, int W, void* scratch, size_t scratch_bytes,
+                 void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (W % 128) return fail(-1, "W must be a multiple of 128");
+  Scratch sc{static_cast<uint8_t*>(scratch), scratch_bytes};
+  ConvLaunch l;
+  memset(&l, 0, sizeof(l));
+  l.dtype = dtype; l.taps = taps;
+  l.nt = pick_nt(taps, Cout);
+  l.cin_pad = round_up(Cin, conv_stage_channels(dtype, taps));
+  l.cout = Cout; l.cout_pad = round_up(Cout, l.nt);
+  if (taps == 9) l.ht = (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
+  else l.ht = H >= 2 ? 2 : 1;
+  if (l.nt == 16 && l.ht != 4) return fail(-1, "small-N conv needs H %% 4 == 0");
+  l.in0 = make_pt(sc, dtype, B, l.cin_pad, H, W, 0);
+  l.out = make_pt(sc, dtype, B, l.cout_pad, H, W, 0);
+  PT res = make_pt(sc, dtype, B, l.cout_pad, H, W, 0);
+  void* wp = sc.take(conv_packed_weight_bytes(dtype, taps, l.nt, l.cin_pad, l.cout_pad));
+  float* bp = static_cast<float*>(sc.take(static_cast<size_t>(l.cout_pad) * 4));
+  if (!l.in0.ptr || !l.out.ptr || !res.ptr || !wp || !bp) return fail(-1, "scratch too small");
+  CUDA_TRY(cudaMemsetAsync(l.in0.ptr, 0, l.in0.bytes(dtype), s));
+  CUDA_TRY(pack_nchw(dtype, x, B, Cin, H, W, l.in0, 0, s));
+  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s));
+  CUDA_TRY(cudaMemsetAsync(bp, 0, static_cast<size_t>(l.cout_pad) * 4, s));
+  if (bias) CUDA_TRY(cudaMemcpyAsync(bp, bias, static_cast<size_t>(Cout) * 4, cudaMemcpyDeviceToDevice, s));
+  if (residual) {
+    CUDA_TRY(cudaMemsetAsync(res.ptr, 0, res.bytes(dtype), s));
+    CUDA_TRY(pack_nchw(dtype, residual, B, Cout, H, W, res, 0, s));
+    l.residual = res.ptr;
+  }
+  l.wpacked = wp; l.bias = bp; l.scale = scale;
+  int rc = conv_make_tmaps(l);
+  if (rc) return fail(-4, "tensor map encode failed (%d)", rc);
+  CUDA_TRY(conv_launch(l, s));
+  CUDA_TRY(unpack_nchw(dtype, l.out, y, 0, Cout, s));
+  return 0;
+}
+
+int r2dm_op_groupnorm(int dtype, const float* x, const float* gamma, const float* beta, const float* film,
+                      float eps, int silu, float* y, int B, int C, int H, int W, void* scratch,
+                      size_t scratch_bytes, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (C % (kNU * dtype_cw(dtype))) return fail(-1, "C must be a multiple of %d", kNU * dtype_cw(dtype));
+  Scratch sc{static_cast<uint8_t*>(scratch), scratch_bytes};
+  PT probe; probe.B = B; probe.C = C; probe.H = H; probe.W = W;
+  PT in = make_pt(sc, dtype, B, C, H, W, tensor_stats_slots(dtype, probe));
+  PT out = make_pt(sc, dtype, B, C, H, W, 0);
+  if (!in.ptr || !out.ptr || !in.stats) return fail(-1, "scratch too small");
+  CUDA_TRY(pack_nchw(dtype, x, B, C, H, W, in, 0, s));
+  CUDA_TRY(tensor_stats_launch(dtype, in, s));
+  GnApply g;
+  memset(&g, 0, sizeof(g));
+  g.dtype = dtype; g.src0 = in; g.dst = out; g.groups = kNU; g.eps = eps; g.silu = silu;
+  if (film) {
+    g.film = film; g.film_stride = 2 * C; g.film_off = 0; g.row_batch_stride = 1; g.rows_per_step = 0;
+  } else {
+    g.gamma = gamma; g.beta = beta;
+  }
+  CUDA_TRY(gn_apply_launch(g, s));
+  CUDA_TRY(unpack_nchw(dtype, out, y, 0, C, s));
+  return 0;
+}
+
+int r2dm_op_resample(int dtype, int dir, const float* x, float* y, int B, int C, int H, int W, void* scratch,
+                     size_t scratch_bytes, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (C % dtype_cw(dtype)) return fail(-1, "C must be a multiple of %d", dtype_cw(dtype));
+  Scratch sc{static_cast<uint8_t*>(scratch), scratch_bytes};
+  PT in = make_pt(sc, dtype, B, C, H, W, 0);
+  const int Ho = dir > 0 ? H * 2 : H / 2, Wo = dir > 0 ? W * 2 : W / 2;
+  PT out = make_pt(sc, dtype, B, C, Ho, Wo, 0);
+  if (!in.ptr || !out.ptr) return fail(-1, "scratch too small");
+  CUDA_TRY(pack_nchw(dtype, x, B, C, H, W, in, 0, s));
+  if (dir > 0) CUDA_TRY(up2_launch(dtype, in, out, s));
+  else CUDA_TRY(down2_launch(dtype, in, out, s));
+  CUDA_TRY(unpack_nchw(dtype, out, y, 0, C, s));
+  return 0;
+}
+
+int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int heads, int H, int W, void* scratch,
+                      size_t scratch_bytes, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Scratch sc{static_cast<uint8_t*>(scratch), scratch_bytes};
+  PT in = make_pt(sc, dtype, B, 3 * E, H, W, 0);
+  PT out = make_pt(sc, dtype, B, E, H, W, 0);
+  if (!in.ptr || !out.ptr) return fail(-1, "scratch too small");
+  CUDA_TRY(pack_nchw(dtype, qkv, B, 3 * E, H, W, in, 0, s));
+  CUDA_TRY(attention_launch(dtype, in, out, heads, s));
+  CUDA_TRY(unpack_nchw(dtype, out, y, 0, E, s));
+  return 0;
+}
+
+int r2dm_debug_tensor(r2dm_handle h, const char* name, float* out, int* C, int* H, int* W, void* stream) {
+  if (!h || !name) return fail(-1, "null argument");
+  auto it = h->named.find(name);
+  if (it == h->named.end()) return fail(-5, "no tensor named %s", name);
+  const PT& t = it->second;
+  if (C) *C = t.C;
+  if (H) *H = t.H;
+  if (W) *W = t.W;
+  if (out) CUDA_TRY(unpack_nchw(h->dtype, t, out, 0, t.C, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // extern "C"

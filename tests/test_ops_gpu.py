@@ -1,0 +1,120 @@
+"""Per-kernel parity: CUDA kernels (through the C ABI op hooks) vs the CPU oracle.
+
+Tolerances.  The tensor-core path multiplies bf16 (or tf32) operands exactly and accumulates in
+fp32, so when the inputs are pre-rounded to the operand type the only error left is the fp32
+accumulation order (~1e-6) plus the rounding of the stored output (bf16: 2^-9 relative).
+  fp32/tf32 mode : l2-rel <= 2e-5
+  bf16 mode      : l2-rel <= 4e-3, max-abs <= 2^-7 * max|y|
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import r2dm_oracle as O
+from tests.helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _round_to(x, dtype):
+    if dtype == "bf16":
+        return x.bfloat16().float()
+    # tf32: keep 10 mantissa bits (exactly representable inputs make the tensor-core read exact)
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def _check(y, ref, dtype, name):
+    e = rel_l2(y, ref)
+    tol = 4e-3 if dtype == "bf16" else 2e-5
+    assert e <= tol, f"{name}[{dtype}]: l2-rel {e:.3e} > {tol}"
+    if dtype == "bf16":
+        m = (y.cpu() - ref).abs().max().item()
+        assert m <= 2 ** -7 * ref.abs().max().item() + 1e-6, f"{name}[{dtype}]: max-abs {m:.3e}"
+
+
+CONV_CASES = [
+    # B, Cin, Cout, H, W, k, residual
+    (2, 64, 64, 8, 256, 3, True),
+    (1, 34, 64, 4, 128, 3, False),
+    (2, 128, 128, 4, 128, 3, True),
+    (1, 64, 2, 4, 128, 3, False),
+    (1, 256, 64, 2, 256, 3, False),
+    (1, 64, 128, 6, 128, 3, False),
+    (2, 128, 64, 4, 128, 1, False),
+    (1, 512, 1536, 2, 128, 1, False),
+    (1, 256, 256, 2, 128, 1, True),
+]
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv(case, dtype):
+    from r2dm_b200 import ops
+    B, Cin, Cout, H, W, k, use_res = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = _round_to(torch.randn(B, Cin, H, W, generator=g), dtype)
+    w = _round_to(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k), dtype)
+    b = torch.randn(Cout, generator=g) * 0.1
+    res = _round_to(torch.randn(B, Cout, H, W, generator=g), dtype) if use_res else None
+    scale = 1 / math.sqrt(2) if use_res else 1.0
+    ref = O.ring_conv3x3(x, w, b) if k == 3 else O.conv1x1(x, w, b)
+    if use_res:
+        ref = (ref + res) * scale
+    y = ops.conv2d(x.cuda(), w.cuda(), b.cuda(), res.cuda() if use_res else None, scale, dtype=dtype)
+    torch.cuda.synchronize()
+    _check(y, ref, dtype, f"conv{k}x{k} {case}")
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("film", [False, True])
+@pytest.mark.parametrize("shape", [(2, 64, 4, 128), (1, 128, 8, 256), (2, 512, 2, 128)])
+def test_groupnorm_silu(shape, film, dtype):
+    from r2dm_b200 import ops
+    B, Cc, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    x = _round_to(torch.randn(B, Cc, H, W, generator=g) * 1.7 + 0.4, dtype)
+    if film:
+        ss = torch.randn(B, 2 * Cc, generator=g) * 0.3
+        h = O.group_norm(x, 8, 1e-6, None, None)
+        ref = torch.nn.functional.silu(h * (1 + ss[:, :Cc, None, None]) + ss[:, Cc:, None, None])
+        y = ops.group_norm(x.cuda(), film=ss.cuda(), eps=1e-6, silu=True, dtype=dtype)
+    else:
+        gm, bt = 1 + 0.1 * torch.randn(Cc, generator=g), 0.1 * torch.randn(Cc, generator=g)
+        ref = torch.nn.functional.silu(O.group_norm(x, 8, 1e-6, gm, bt))
+        y = ops.group_norm(x.cuda(), gm.cuda(), bt.cuda(), eps=1e-6, silu=True, dtype=dtype)
+    torch.cuda.synchronize()
+    _check(y, ref, dtype, f"groupnorm {shape} film={film}")
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("shape", [(2, 64, 4, 256), (1, 128, 8, 512)])
+def test_resample(shape, dtype):
+    from r2dm_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = _round_to(torch.randn(*shape, generator=g), dtype)
+    yd = ops.resample(x.cuda(), down=2, dtype=dtype)
+    yu = ops.resample(x.cuda(), up=2, dtype=dtype)
+    torch.cuda.synchronize()
+    _check(yd, O.resample_down2(x), dtype, "down2")
+    _check(yu, O.resample_up2(x), dtype, "up2")
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("case", [(2, 256, 8, 2, 128), (1, 512, 8, 4, 128)])
+def test_attention_core(case, dtype):
+    from r2dm_b200 import ops
+    B, E, heads, H, W = case
+    hd = E // heads
+    g = torch.Generator().manual_seed(9)
+    qkv = _round_to(torch.randn(B, 3 * E, H, W, generator=g), dtype)
+    y = ops.attention_core(qkv.cuda(), heads, dtype=dtype)
+    torch.cuda.synchronize()
+    tok = qkv.flatten(2).transpose(1, 2)
+    q, k, v = tok.split(E, dim=-1)
+    q = q.reshape(B, -1, heads, hd).transpose(1, 2)
+    k = k.reshape(B, -1, heads, hd).transpose(1, 2)
+    v = v.reshape(B, -1, heads, hd).transpose(1, 2)
+    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(B, -1, E).transpose(1, 2).reshape(B, E, H, W)
+    _check(y, ref, dtype, f"attention {case}")
