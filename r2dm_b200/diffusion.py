@@ -1,0 +1,527 @@
+"""Gaussian diffusion samplers — host-side mirror of models/diffusion/{base,continuous_time,
+discrete_time}.py of the reference, driving the CUDA U-Net and the fused sampler-update kernels.
+
+Public protocol kept from the reference: `sample`, `repaint`, `p_step`, `q_step`,
+`q_step_from_x_0`, `randn`, `randn_like`, `log_snr`, `device`, `sampling_shape`, `model(x, cond)`,
+`load_state_dict` of reference checkpoints (keys `model.*`, `_dummy`, discrete-time tables).
+Training-only members (`p_loss`, `forward`, `get_target`, `get_loss_weight`, `sample_timesteps`) are
+out of scope and raise NotImplementedError.
+
+How the hot loop runs (no host sync between steps):
+  * the network condition of step i depends only on i, so the time-embedding MLP and all 24 AdaGN
+    projections are evaluated for all N steps up front into a FiLM table [N, F] (one kernel pair);
+  * the per-step scalar algebra of p_step (alpha/sigma, x0 coefficients, DDPM/DDIM update) is folded
+    on the host, in fp64, into a coefficient table [N, 5(+2)];
+  * one step = U-Net forward + fused update + counter increment, captured once in a CUDA graph and
+    replayed N times; the kernels pick their table row through a device-side step counter;
+  * noise is drawn exactly like the reference does (`torch.randn(C,H,W, generator=g_i)` per sample
+    per step, base.py:71-94) straight into the graph's static noise buffer, so the RNG stream is
+    identical to the reference's on the same device type.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+try:  # progress bars are optional plumbing
+    from tqdm.auto import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, **kwargs):
+        return it
+
+
+# ------------------------------------------------------------------------------------- schedules
+def _log(t: torch.Tensor, eps: float = 1e-20) -> torch.Tensor:
+    return torch.log(t.clamp(min=eps))
+
+
+def _log_snr_schedule_linear(t: torch.Tensor) -> torch.Tensor:
+    """continuous_time.py:18-19."""
+    return -_log(torch.special.expm1(1e-4 + 10 * (t ** 2)))[:, None, None, None]
+
+
+def _log_snr_schedule_cosine(t: torch.Tensor, logsnr_min: float = -15, logsnr_max: float = 15) -> torch.Tensor:
+    """continuous_time.py:22-29: lambda(t) = -2 log tan(t_min + t (t_max - t_min))."""
+    t_min = math.atan(math.exp(-0.5 * logsnr_max))
+    t_max = math.atan(math.exp(-0.5 * logsnr_min))
+    return -2 * _log(torch.tan(t_min + t * (t_max - t_min)))[:, None, None, None]
+
+
+def _log_snr_schedule_cosine_shifted(t, image_d, noise_d, logsnr_min=-15, logsnr_max=15):
+    """continuous_time.py:32-41."""
+    return _log_snr_schedule_cosine(t, logsnr_min, logsnr_max) + 2 * math.log(noise_d / image_d)
+
+
+def _log_snr_schedule_cosine_interpolated(t, image_d, noise_d_low, noise_d_high, logsnr_min=-15, logsnr_max=15):
+    """continuous_time.py:44-58."""
+    low = _log_snr_schedule_cosine_shifted(t, image_d, noise_d_low, logsnr_min, logsnr_max)
+    high = _log_snr_schedule_cosine_shifted(t, image_d, noise_d_high, logsnr_min, logsnr_max)
+    tt = t[:, None, None, None]
+    return tt * low + (1 - tt) * high
+
+
+def _log_snr_to_alpha_sigma(log_snr: torch.Tensor):
+    """continuous_time.py:61-63."""
+    return log_snr.sigmoid().sqrt(), (-log_snr).sigmoid().sqrt()
+
+
+def continuous_coefficients(lam_t: torch.Tensor, lam_s: torch.Tensor, mode: str, eta: float,
+                            objective: str) -> torch.Tensor:
+    """Fold continuous_time.py:203-229 into per-row scalars [n, 5] = (ux, up, kx, k0, kn):
+        x0 = clamp(ux x_t + up pred);  x_s = kx x_t + k0 x0 + kn noise.   Evaluated in fp64."""
+    lt, ls = lam_t.double().flatten(), lam_s.double().flatten()
+    a_t, s_t = _log_snr_to_alpha_sigma(lt)
+    a_s, s_s = _log_snr_to_alpha_sigma(ls)
+    if objective == "eps":
+        ux, up = 1 / a_t, -s_t / a_t
+    elif objective == "v":
+        ux, up = a_t, -s_t
+    elif objective == "x_0":
+        ux, up = torch.zeros_like(a_t), torch.ones_like(a_t)
+    else:
+        raise ValueError(f"invalid objective {objective}")
+    if mode == "ddpm":
+        c = -torch.special.expm1(lt - ls)
+        kx, k0, kn = a_s * (1 - c) / a_t, a_s * c, s_s * c.sqrt()
+    elif mode == "ddim":
+        c1 = eta * s_s / s_t * (1 - a_t ** 2 / a_s ** 2).clamp(min=0).sqrt()
+        c2 = (1 - a_s ** 2 - c1 ** 2).clamp(min=0).sqrt()
+        kx, k0, kn = c2 / s_t, a_s - c2 * a_t / s_t, c1
+    else:
+        raise ValueError(f"invalid mode {mode}")
+    return torch.stack([ux, up, kx, k0, kn], dim=1)
+
+
+# ------------------------------------------------------------------------------------- base
+class GaussianDiffusion(nn.Module):
+    """Mirror of models/diffusion/base.py:9-163 (sampling members only)."""
+
+    def __init__(
+        self,
+        model: nn.Module,
+        sampling: str = "ddpm",
+        prediction_type: str = "eps",
+        loss_type="l2",
+        num_training_steps: Optional[int] = 1000,
+        noise_schedule: str = "linear",
+        min_snr_loss_weight: bool = True,
+        min_snr_gamma: float = 5.0,
+        sampling_resolution=None,
+        clip_sample: bool = True,
+        clip_sample_range: float = 1,
+    ):
+        super().__init__()
+        self.model = model
+        self.sampling = sampling
+        self.num_training_steps = num_training_steps
+        self.objective = prediction_type
+        self.noise_schedule = noise_schedule
+        self.min_snr_loss_weight = min_snr_loss_weight
+        self.min_snr_gamma = min_snr_gamma
+        self.clip_sample = clip_sample
+        self.clip_sample_range = clip_sample_range
+        self.loss_type = loss_type
+        if prediction_type not in ("eps", "v", "x_0"):
+            raise ValueError(f"invalid objective {prediction_type}")
+        if sampling_resolution is None:
+            assert hasattr(self.model, "resolution")
+            assert hasattr(self.model, "in_channels")
+            self.sampling_shape = (self.model.in_channels, *self.model.resolution)
+        else:
+            assert len(sampling_resolution) == 2
+            assert hasattr(self.model, "in_channels")
+            self.sampling_shape = (self.model.in_channels, *sampling_resolution)
+        self.use_cuda_graph = True
+        self._graphs = {}
+        self.setup_parameters()
+        self.register_buffer("_dummy", torch.tensor([]))
+
+    @property
+    def device(self):
+        return self._dummy.device
+
+    # -- random draws: base.py:71-94 ------------------------------------------------------------
+    def randn(self, *shape, rng=None, out: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        """None / one Generator / list of per-sample Generators (len == batch).  Generators living on
+        another device (e.g. CPU generators with a CUDA model) draw on their own device and are
+        copied over, which makes CPU-reference trajectories reproducible on the GPU."""
+        dev = kwargs.pop("device", None)
+        dtype = kwargs.pop("dtype", torch.float32)
+
+        def draw(shp, gen):
+            gdev = gen.device if gen is not None else dev
+            t = torch.randn(*shp, generator=gen, device=gdev, dtype=dtype)
+            return t
+
+        if rng is None:
+            res = draw(shape, None)
+        elif isinstance(rng, torch.Generator):
+            res = draw(shape, rng)
+        elif isinstance(rng, list):
+            assert len(rng) == shape[0]
+            if out is not None and all(r.device == out.device for r in rng):
+                for i, r in enumerate(rng):
+                    torch.randn(*shape[1:], generator=r, out=out[i])
+                return out
+            res = torch.stack([draw(shape[1:], r) for r in rng])
+        else:
+            raise ValueError(f"invalid rng: {rng}")
+        if out is not None:
+            out.copy_(res, non_blocking=True)
+            return out
+        return res.to(dev) if dev is not None else res
+
+    def randn_like(self, x: torch.Tensor, rng=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.randn(*x.shape, rng=rng, out=out, device=x.device, dtype=x.dtype)
+
+    # -- training-only API: out of scope ----------------------------------------------------------
+    def setup_parameters(self) -> None:
+        raise NotImplementedError
+
+    def _training_only(self, *a, **k):
+        raise NotImplementedError("training (p_loss / forward) is outside the scope of r2dm_b200; "
+                                  "this package accelerates the sampling path only")
+
+    p_loss = forward = get_target = get_loss_weight = sample_timesteps = _training_only
+
+    # -- engine helpers ---------------------------------------------------------------------------
+    def _engine(self):
+        return self.model.engine()
+
+    def _clip(self) -> float:
+        return float(self.clip_sample_range) if self.clip_sample else 0.0
+
+    def _update(self, x_out, x, pred, noise, coef, step_ptr, rows_per_step, row_batch_stride,
+                known=None, mask=None, noise2=None):
+        B = x.shape[0]
+        per = x[0].numel()
+        L.check(L.lib().r2dm_sampler_update(
+            L.ptr(x_out), L.ptr(x), L.ptr(pred), L.ptr(noise), L.ptr(coef), coef.shape[1],
+            L.ptr(step_ptr) if step_ptr is not None else None, rows_per_step, row_batch_stride,
+            self._clip(), L.ptr(known) if known is not None else None,
+            L.ptr(mask) if mask is not None else None, L.ptr(noise2) if noise2 is not None else None,
+            B, per, L.stream_ptr()), "r2dm_sampler_update")
+        return x_out
+
+    def _axpby(self, x, noise, ac):
+        y = torch.empty_like(x)
+        L.check(L.lib().r2dm_axpby(L.ptr(y), L.ptr(x), L.ptr(noise), L.ptr(ac), x.shape[0], x[0].numel(),
+                                   L.stream_ptr()), "r2dm_axpby")
+        return y
+
+    def _run_table(self, x, conds, coefs, rng, return_all, progress, desc, draw_noise):
+        """Shared hot loop: N steps over precomputed (cond, coefficient) tables with a device-side
+        step counter; one CUDA graph per (batch, precision) replayed every step."""
+        eng = self._engine()
+        dev = x.device
+        N = conds.numel()
+        with torch.cuda.device(dev):
+            film = eng.cond_embed(conds.to(dev))
+            coef = coefs.to(device=dev, dtype=torch.float32).contiguous()
+            step = torch.zeros(1, dtype=torch.int32, device=dev)
+            x = L.f32c(x).clone()
+            pred = torch.empty_like(x)
+            noise = torch.empty_like(x)
+            out = [x.clone()] if return_all else None
+            lib = L.lib()
+
+            def one_step():
+                eng.forward_film(x, film, pred, step_ptr=step, rows_per_step=1, row_batch_stride=0)
+                self._update(x, x, pred, noise, coef, step, 1, 0)
+                L.check(lib.r2dm_advance_step(L.ptr(step), 1, L.stream_ptr()))
+
+            graph = None
+            start = 0
+            if self.use_cuda_graph and N > 2:
+                # the first step runs eagerly (lazy kernel attribute setup), then capture
+                if draw_noise:
+                    self.randn_like(x, rng=rng, out=noise)
+                else:
+                    noise.zero_()
+                one_step()
+                if return_all:
+                    out.append(x.clone())
+                start = 1
+                torch.cuda.current_stream().synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    one_step()
+                # capture does not execute: the counter still points at step 1
+            for _ in tqdm(range(start, N), desc=desc, leave=False, disable=not progress):
+                if draw_noise:
+                    self.randn_like(x, rng=rng, out=noise)
+                if graph is not None:
+                    graph.replay()
+                else:
+                    one_step()
+                if return_all:
+                    out.append(x.clone())
+        return torch.stack(out) if return_all else x
+
+
+# ------------------------------------------------------------------------------------- continuous
+class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
+    """Mirror of models/diffusion/continuous_time.py:66-317 (https://arxiv.org/abs/2107.00630)."""
+
+    def __init__(
+        self,
+        model: nn.Module,
+        prediction_type: str = "eps",
+        loss_type="l2",
+        noise_schedule: str = "cosine",
+        min_snr_loss_weight: bool = True,
+        min_snr_gamma: float = 5.0,
+        sampling_resolution=None,
+        clip_sample: bool = True,
+        clip_sample_range: float = 1,
+        image_d: float = None,
+        noise_d_low: float = None,
+        noise_d_high: float = None,
+    ):
+        # (the reference assigns these after super().__init__, which makes its shifted /
+        #  interpolated schedules unconstructible, continuous_time.py:89-123; here they work)
+        self._sched_args = dict(image_d=image_d, noise_d_low=noise_d_low, noise_d_high=noise_d_high)
+        super().__init__(
+            model=model, sampling="ddpm", prediction_type=prediction_type, loss_type=loss_type,
+            num_training_steps=None, noise_schedule=noise_schedule, min_snr_loss_weight=min_snr_loss_weight,
+            min_snr_gamma=min_snr_gamma, sampling_resolution=sampling_resolution, clip_sample=clip_sample,
+            clip_sample_range=clip_sample_range)
+        self.image_d, self.noise_d_low, self.noise_d_high = image_d, noise_d_low, noise_d_high
+
+    def setup_parameters(self) -> None:
+        a = self._sched_args
+        if self.noise_schedule == "linear":
+            self.log_snr = _log_snr_schedule_linear
+        elif self.noise_schedule == "cosine":
+            self.log_snr = _log_snr_schedule_cosine
+        elif self.noise_schedule == "cosine_shifted":
+            assert a["image_d"] is not None and a["noise_d_low"] is not None
+            self.log_snr = partial(_log_snr_schedule_cosine_shifted, image_d=a["image_d"], noise_d=a["noise_d_low"])
+        elif self.noise_schedule == "cosine_interpolated":
+            assert a["image_d"] is not None and a["noise_d_low"] is not None and a["noise_d_high"] is not None
+            self.log_snr = partial(_log_snr_schedule_cosine_interpolated, image_d=a["image_d"],
+                                   noise_d_low=a["noise_d_low"], noise_d_high=a["noise_d_high"])
+        else:
+            raise ValueError(f"invalid beta schedule: {self.noise_schedule}")
+
+    def get_network_condition(self, steps):
+        return self.log_snr(steps)[:, 0, 0, 0]
+
+    def _lam(self, t: torch.Tensor) -> torch.Tensor:
+        """fp32 log-SNR of times t ([n]) evaluated on the host like the reference evaluates it."""
+        return self.log_snr(t.detach().float().cpu())[:, 0, 0, 0]
+
+    # -- forward process ---------------------------------------------------------------------------
+    def q_step_from_x_0(self, x_0, step_t, rng=None):
+        """continuous_time.py:169-176: x_t = alpha x_0 + sigma eps; returns (x_t, eps)."""
+        x_0 = L.f32c(x_0)
+        noise = self.randn_like(x_0, rng=rng)
+        alpha, sigma = _log_snr_to_alpha_sigma(self._lam(step_t).double())
+        ac = torch.stack([alpha, sigma], dim=1).float().to(x_0.device)
+        with torch.cuda.device(x_0.device):
+            return self._axpby(x_0, noise, ac), noise
+
+    def q_step(self, x_s, step_t, step_s, rng=None):
+        """continuous_time.py:178-190: q(z_t | z_s), 0 < s < t < 1."""
+        x_s = L.f32c(x_s)
+        a_t, s_t = _log_snr_to_alpha_sigma(self._lam(step_t).double())
+        a_s, s_s = _log_snr_to_alpha_sigma(self._lam(step_s).double())
+        a_ts = a_t / a_s
+        var = s_t ** 2 - a_ts ** 2 * s_s ** 2
+        noise = self.randn_like(x_s, rng=rng)
+        ac = torch.stack([a_ts, var.clamp(min=0).sqrt()], dim=1).float().to(x_s.device)
+        with torch.cuda.device(x_s.device):
+            return self._axpby(x_s, noise, ac)
+
+    # -- reverse process ---------------------------------------------------------------------------
+    @torch.inference_mode()
+    def p_step(self, x_t, step_t, step_s, rng=None, mode="ddpm", ddim_eta: float = 0.0,
+               _known=None, _mask=None):
+        """continuous_time.py:192-232: one reverse step p(z_s | z_t) with per-sample times."""
+        if mode not in ("ddpm", "ddim"):
+            raise ValueError(f"invalid mode {mode}")
+        x_t = L.f32c(x_t)
+        lam_t, lam_s = self._lam(step_t), self._lam(step_s)
+        coef = continuous_coefficients(lam_t, lam_s, mode, ddim_eta, self.objective)
+        eng = self._engine()
+        with torch.cuda.device(x_t.device):
+            noise2 = None
+            if _known is not None:  # RePaint: the known-region draw comes first (continuous_time.py:296)
+                noise2 = self.randn_like(x_t, rng=rng)
+                a_s, s_s = _log_snr_to_alpha_sigma(lam_s.double())
+                coef = torch.cat([coef, a_s[:, None], s_s[:, None]], dim=1)
+            film = eng.cond_embed(lam_t.to(x_t.device))
+            pred = torch.empty_like(x_t)
+            eng.forward_film(x_t, film, pred, step_ptr=None, rows_per_step=0, row_batch_stride=1)
+            noise = self.randn_like(x_t, rng=rng)
+            coef = coef.float().contiguous().to(x_t.device)
+            x_s = torch.empty_like(x_t)
+            self._update(x_s, x_t, pred, noise, coef, None, 0, 1, _known, _mask, noise2)
+        return x_s
+
+    @torch.inference_mode()
+    def sample(self, batch_size: int, num_steps: int, progress: bool = True, rng=None,
+               return_all: bool = False, mode: str = "ddpm", ddim_eta: float = 0.0):
+        """continuous_time.py:234-258."""
+        if mode not in ("ddpm", "ddim"):
+            raise ValueError(f"invalid mode {mode}")
+        x = self.randn(batch_size, *self.sampling_shape, rng=rng, device=self.device)
+        steps = torch.linspace(1.0, 0.0, num_steps + 1)
+        lam = self._lam(steps)
+        coefs = continuous_coefficients(lam[:-1], lam[1:], mode, ddim_eta, self.objective)
+        return self._run_table(x, lam[:-1], coefs, rng, return_all, progress, "sampling", draw_noise=True)
+
+    @torch.inference_mode()
+    def repaint(self, known, mask, num_steps: int, num_resample_steps: int = 1, jump_length: int = 1,
+                progress: bool = True, rng=None, return_all: bool = False):
+        """continuous_time.py:260-317 (RePaint, https://arxiv.org/abs/2201.09865); mask == 1 is known."""
+        assert num_resample_steps > 0
+        assert jump_length > 0
+        batch_size = known.shape[0]
+        known = L.f32c(known.to(self.device))
+        mask = L.f32c(mask.to(self.device).expand_as(known))
+        x_t = self.randn(batch_size, *self.sampling_shape, rng=rng, device=self.device)
+        steps = torch.linspace(1, 0, num_steps + 1)[None].repeat_interleave(batch_size, dim=0)
+        out = [x_t] if return_all else None
+        x_s = None
+        for i in tqdm(range(num_steps), desc="RePaint", leave=False, disable=not progress):
+            for j in range(num_resample_steps):
+                step_t, step_s = steps[:, [i]], steps[:, [i + 1]]
+                interp = torch.linspace(0, 1, jump_length + 1)
+                r_steps = step_t + interp[None] * (step_s - step_t)
+                x = x_t
+                for k in range(jump_length):   # t -> s, known region re-noised and blended in-kernel
+                    x = self.p_step(x, r_steps[:, k], r_steps[:, k + 1], rng=rng, _known=known, _mask=mask)
+                x_s = x
+                if return_all:
+                    out.append(x_s)
+                if (i == num_steps - 1) or (j == num_resample_steps - 1):
+                    x_t = x
+                    break
+                x = x_s
+                for k in range(jump_length, 0, -1):   # s -> t
+                    x = self.q_step(x, r_steps[:, k - 1], r_steps[:, k], rng=rng)
+                x_t = x
+        return torch.stack(out) if return_all else x_s
+
+
+# ------------------------------------------------------------------------------------- discrete
+def _linear_beta_schedule(steps):
+    scale = 1000 / steps
+    return torch.linspace(scale * 0.0001, scale * 0.02, steps, dtype=torch.float64)
+
+
+def _alpha_bar_to_beta(alphas_bar):
+    alphas_bar = alphas_bar / alphas_bar[0]
+    return torch.clip(1 - (alphas_bar[1:] / alphas_bar[:-1]), 0, 0.999)
+
+
+def _cosine_beta_schedule(steps, s=0.008):
+    t = torch.linspace(0, steps, steps + 1, dtype=torch.float64) / steps
+    return _alpha_bar_to_beta(torch.cos((t + s) / (1 + s) * math.pi * 0.5) ** 2)
+
+
+def _sigmoid_beta_schedule(steps, start=-3, end=3, tau=1):
+    t = torch.linspace(0, steps, steps + 1, dtype=torch.float64) / steps
+    v0, v1 = torch.tensor(start / tau).sigmoid(), torch.tensor(end / tau).sigmoid()
+    return _alpha_bar_to_beta((-((t * (end - start) + start) / tau).sigmoid() + v1) / (v1 - v0))
+
+
+class DiscreteTimeGaussianDiffusion(GaussianDiffusion):
+    """Mirror of models/diffusion/discrete_time.py:51-201 (https://arxiv.org/abs/2006.11239)."""
+
+    def setup_parameters(self) -> None:
+        assert self.num_training_steps is not None
+        if self.noise_schedule == "linear":
+            beta = _linear_beta_schedule(self.num_training_steps)
+        elif self.noise_schedule == "cosine":
+            beta = _cosine_beta_schedule(self.num_training_steps)
+        elif self.noise_schedule == "sigmoid":
+            beta = _sigmoid_beta_schedule(self.num_training_steps)
+        else:
+            raise ValueError(f"invalid beta schedule {self.noise_schedule}")
+        beta = beta[:, None, None, None]
+        alpha_bar = torch.cumprod(1 - beta, dim=0)
+        alpha_bar_prev = torch.cat([torch.ones_like(alpha_bar[:1]), alpha_bar[:-1]])
+        self.register_buffer("beta", beta.float())
+        self.register_buffer("alpha_bar", alpha_bar.float())
+        self.register_buffer("alpha_bar_prev", alpha_bar_prev.float())
+        self.register_buffer("snr", (alpha_bar / (1 - alpha_bar)).float())
+
+    def get_network_condition(self, steps: torch.Tensor) -> torch.Tensor:
+        return steps
+
+    def _coefficients(self, steps: torch.Tensor, mode: str, eta: float) -> torch.Tensor:
+        """discrete_time.py:135-179 folded into (ux, up, kx, k0, kn) rows, fp64."""
+        idx = steps.detach().long().cpu()
+        beta = self.beta.flatten().cpu().double()[idx]
+        ab = self.alpha_bar.flatten().cpu().double()[idx]
+        abp = self.alpha_bar_prev.flatten().cpu().double()[idx]
+        alpha = 1 - beta
+        nz = (idx != 0).double()
+        if self.objective == "eps":
+            ux, up = ab.rsqrt(), -(ab.reciprocal() - 1).sqrt()
+        elif self.objective == "x_0":
+            ux, up = torch.zeros_like(ab), torch.ones_like(ab)
+        elif self.objective == "v":
+            ux, up = ab.sqrt(), -(1 - ab).sqrt()
+        else:
+            raise ValueError(f"invalid objective {self.objective}")
+        if mode == "ddpm":
+            k0 = abp.sqrt() * beta / (1 - ab)
+            kx = (1 - abp) * alpha.sqrt() / (1 - ab)
+            var = (beta * (1 - abp) / (1 - ab)).clamp(min=1e-20)
+            kn = (0.5 * var.log()).exp() * nz
+        elif mode == "ddim":
+            var = (1 - abp) / (1 - ab) * (1 - ab / abp)
+            std = eta * var.clamp(min=0).sqrt()
+            c2 = (1 - abp - std ** 2).clamp(min=0).sqrt()
+            kx = c2 / (1 - ab).sqrt()
+            k0 = abp.sqrt() - c2 * ab.sqrt() / (1 - ab).sqrt()
+            kn = std * nz if eta > 0 else torch.zeros_like(std)
+        else:
+            raise ValueError(f"invalid mode {mode}")
+        return torch.stack([ux, up, kx, k0, kn], dim=1)
+
+    def q_step_from_x_0(self, x_0, steps, rng=None):
+        """discrete_time.py:119-124."""
+        x_0 = L.f32c(x_0)
+        noise = self.randn_like(x_0, rng=rng)
+        ab = self.alpha_bar.flatten().cpu().double()[steps.detach().long().cpu()]
+        ac = torch.stack([ab.sqrt(), (1 - ab).sqrt()], dim=1).float().to(x_0.device)
+        with torch.cuda.device(x_0.device):
+            return self._axpby(x_0, noise, ac), noise
+
+    @torch.inference_mode()
+    def p_step(self, x_t, steps, rng=None, mode="ddim", eta: float = 0.0):
+        """discrete_time.py:126-180."""
+        x_t = L.f32c(x_t)
+        coef = self._coefficients(steps, mode, eta).float().contiguous().to(x_t.device)
+        eng = self._engine()
+        with torch.cuda.device(x_t.device):
+            film = eng.cond_embed(steps.to(x_t.device).float())
+            pred = torch.empty_like(x_t)
+            eng.forward_film(x_t, film, pred, step_ptr=None, rows_per_step=0, row_batch_stride=1)
+            draws = mode == "ddpm" or eta > 0   # the reference draws no noise for deterministic DDIM
+            noise = self.randn_like(x_t, rng=rng) if draws else torch.zeros_like(x_t)
+            x_s = torch.empty_like(x_t)
+            self._update(x_s, x_t, pred, noise, coef, None, 0, 1)
+        return x_s
+
+    @torch.inference_mode()
+    def sample(self, batch_size: int, num_steps: int, progress: bool = True, rng=None,
+               return_all: bool = False, mode: str = "ddpm"):
+        """discrete_time.py:182-201 (visits t = num_steps-1 ... 0 without re-spacing, like the reference)."""
+        if mode not in ("ddpm", "ddim"):
+            raise ValueError(f"invalid mode {mode}")
+        x = self.randn(batch_size, *self.sampling_shape, rng=rng, device=self.device)
+        ts = torch.arange(num_steps - 1, -1, -1)
+        coefs = self._coefficients(ts, mode, 0.0)
+        return self._run_table(x, ts.float(), coefs, rng, return_all, progress, "sampling",
+                               draw_noise=(mode == "ddpm"))
