@@ -90,7 +90,7 @@ attention_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ out, int E, 
     float v[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = acc[u * CW + i] * inv;
-    const uint4 pk = Elem<T>::pack(v);
+    const uint4 pk = Elem<T>::pack_mma(v);
     const size_t idx = pt_index(b, planes_out, (h * HD) / CW + u, H, Wp, qy, qx + 1);
     out[idx] = pk;
     if (qx == 0) out[idx + W] = pk;

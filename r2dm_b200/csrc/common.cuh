@@ -29,6 +29,14 @@ struct Elem<float> {
     return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
                       __float_as_uint(v[3]));
   }
+  // for tensors that are only ever read as tcgen05 kind::tf32 operands: round to nearest tf32
+  // (the tensor core itself truncates the 13 low mantissa bits, which is biased)
+  __device__ static __forceinline__ uint4 pack_mma(const float* v) {
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r[i]) : "f"(v[i]));
+    return make_uint4(r[0], r[1], r[2], r[3]);
+  }
 };
 template <>
 struct Elem<__nv_bfloat16> {
@@ -51,6 +59,7 @@ struct Elem<__nv_bfloat16> {
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
   }
+  __device__ static __forceinline__ uint4 pack_mma(const float* v) { return pack(v); }
 };
 
 // index (in 16-byte units) of pixel (y, xp) of plane `pl` of image b

@@ -365,6 +365,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     const int o = nti * nt + co;
     float v = 0.f;
     if (ci < cin && o < cout) v = w[(static_cast<size_t>(o) * cin + ci) * taps + tap];
+    if (sizeof(T) == 4) {  // tf32 operand: round to nearest instead of the tensor core's truncation
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+      v = __uint_as_float(r);
+    }
     dst[i] = static_cast<T>(v);
   }
 }

@@ -23,7 +23,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int Csrc, uint4*
     const int c = pl * CW + i - c_off;
     v[i] = (c >= 0 && c < Csrc) ? src[((static_cast<size_t>(b) * Csrc + c) * H + y) * W + x] : 0.f;
   }
-  const uint4 pk = Elem<T>::pack(v);
+  const uint4 pk = Elem<T>::pack_mma(v);
   const size_t idx = pt_index(b, planes, pl, H, W + 2, y, x + 1);
   dst[idx] = pk;
   if (x == 0) dst[idx + W] = pk;
@@ -92,7 +92,7 @@ __global__ void pack_input_kernel(const float* __restrict__ xin, int Cx, const f
     else if (c < Cx + Ce) t = enc[(static_cast<size_t>(c - Cx) * H + y) * W + x];
     v[i] = t;
   }
-  const uint4 pk = Elem<T>::pack(v);
+  const uint4 pk = Elem<T>::pack_mma(v);
   const size_t idx = pt_index(b, planes, pl, H, W + 2, y, x + 1);
   dst[idx] = pk;
   if (x == 0) dst[idx + W] = pk;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
       const float t = fmaf(v[k], ca[k], cb[k]);
       v[k] = p.silu ? silu_f(t) : t;
     }
-    const uint4 pk = Elem<T>::pack(v);
+    const uint4 pk = Elem<T>::pack_mma(v);
     const size_t idx = pt_index(b, planes_dst, pl, p.H, Wp, y, x + 1);
     p.dst[idx] = pk;
     if (x == 0) p.dst[idx + p.W] = pk;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(128) up2_kernel(const uint4* __restrict__ src,
       for (int i = 0; i < CW; ++i) acc[i] = fmaf(wgt, v[i], acc[i]);
     }
   }
-  const uint4 pk = Elem<T>::pack(acc);
+  const uint4 pk = Elem<T>::pack_mma(acc);
   const size_t idx = pt_index(b, planes, pl, Ho, Wo + 2, yo, xo + 1);
   dst[idx] = pk;
   if (xo == 0) dst[idx + Wo] = pk;

@@ -3,7 +3,9 @@
 Tolerances.  The tensor-core path multiplies bf16 (or tf32) operands exactly and accumulates in
 fp32, so when the inputs are pre-rounded to the operand type the only error left is the fp32
 accumulation order (~1e-6) plus the rounding of the stored output (bf16: 2^-9 relative).
-  fp32/tf32 mode : l2-rel <= 2e-5
+  fp32/tf32 mode : l2-rel <= 2e-5 (conv, down2: fp32 outputs)
+                   l2-rel <= 5e-4 (GroupNorm/AdaGN, up2, attention: their outputs only ever feed a
+                   tensor-core operand and are therefore stored rounded-to-nearest tf32, 2^-11 rel.)
   bf16 mode      : l2-rel <= 4e-3, max-abs <= 2^-7 * max|y|
 """
 import math
@@ -24,9 +26,9 @@ def _round_to(x, dtype):
     return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
-def _check(y, ref, dtype, name):
+def _check(y, ref, dtype, name, tf32_out=False):
     e = rel_l2(y, ref)
-    tol = 4e-3 if dtype == "bf16" else 2e-5
+    tol = 4e-3 if dtype == "bf16" else (5e-4 if tf32_out else 2e-5)
     assert e <= tol, f"{name}[{dtype}]: l2-rel {e:.3e} > {tol}"
     if dtype == "bf16":
         m = (y.cpu() - ref).abs().max().item()
@@ -84,7 +86,7 @@ def test_groupnorm_silu(shape, film, dtype):
         ref = torch.nn.functional.silu(O.group_norm(x, 8, 1e-6, gm, bt))
         y = ops.group_norm(x.cuda(), gm.cuda(), bt.cuda(), eps=1e-6, silu=True, dtype=dtype)
     torch.cuda.synchronize()
-    _check(y, ref, dtype, f"groupnorm {shape} film={film}")
+    _check(y, ref, dtype, f"groupnorm {shape} film={film}", tf32_out=True)
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp32"])
@@ -97,7 +99,7 @@ def test_resample(shape, dtype):
     yu = ops.resample(x.cuda(), up=2, dtype=dtype)
     torch.cuda.synchronize()
     _check(yd, O.resample_down2(x), dtype, "down2")
-    _check(yu, O.resample_up2(x), dtype, "up2")
+    _check(yu, O.resample_up2(x), dtype, "up2", tf32_out=True)
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp32"])
@@ -117,4 +119,4 @@ def test_attention_core(case, dtype):
     v = v.reshape(B, -1, heads, hd).transpose(1, 2)
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
     ref = (att @ v).transpose(1, 2).reshape(B, -1, E).transpose(1, 2).reshape(B, E, H, W)
-    _check(y, ref, dtype, f"attention {case}")
+    _check(y, ref, dtype, f"attention {case}", tf32_out=True)

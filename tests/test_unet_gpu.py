@@ -1,0 +1,81 @@
+"""Whole-network parity: r2dm_b200.EfficientUNet (CUDA, through setup_model + the C ABI) vs the
+golden outputs of the reference (tests/golden/unet.pt) and the CPU oracle.
+
+Tolerances (l2-relative to the fp32 reference output, random weights):
+  fp32 mode (tf32 tensor cores, like the reference's own GPU default): 5e-3
+  bf16 mode (bf16 operands/storage, fp32 accumulate/statistics):                           3e-2
+    (the reference's own bf16-autocast forward sits at 2.4e-2 vs fp64)
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import r2dm_oracle as O
+from tests.helpers import GOLDEN, H_CFG, SMALL_CFG, rel_l2
+from tests.util_model import make_ddpm
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 5e-3, "bf16": 3e-2}
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(os.path.join(GOLDEN, "unet.pt"))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["small", "H"])
+def test_forward_matches_reference_golden(golden, tag, precision):
+    cfg, B = (SMALL_CFG, 2) if tag == "small" else (H_CFG, 1)
+    gd = golden[tag]
+    sd = O.random_state_dict(cfg, gd["seed_weights"])
+    ddpm = make_ddpm(cfg, sd, precision=precision)
+    g = torch.Generator().manual_seed(gd["seed_x"])
+    x = torch.randn(B, cfg.in_channels, *cfg.resolution, generator=g)
+    y = ddpm.model(x.cuda(), gd["cond"].cuda())
+    torch.cuda.synchronize()
+    assert y.shape == gd["y"].shape and y.dtype == torch.float32
+    e = rel_l2(y, gd["y"])
+    assert e <= TOL[precision], f"{tag}/{precision}: l2-rel {e:.3e}"
+
+
+def test_batch_composition_invariance():
+    """Sample i's prediction must not depend on its batch neighbours."""
+    cfg = SMALL_CFG
+    sd = O.random_state_dict(cfg, 3)
+    ddpm = make_ddpm(cfg, sd, precision="bf16")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 2, *cfg.resolution, generator=g).cuda()
+    cond = torch.tensor([-2.0, 0.5, 7.0]).cuda()
+    y3 = ddpm.model(x, cond)
+    y1 = ddpm.model(x[1:2].contiguous(), cond[1:2])
+    torch.cuda.synchronize()
+    assert torch.equal(y3[1:2], y1), "batch split changed a sample's result"
+
+
+def test_scalar_timestep_broadcast_and_autocast():
+    cfg = SMALL_CFG
+    sd = O.random_state_dict(cfg, 3)
+    ddpm = make_ddpm(cfg, sd, precision="fp32")
+    x = torch.randn(2, 2, *cfg.resolution).cuda()
+    ya = ddpm.model(x, torch.tensor(1.5).cuda())
+    yb = ddpm.model(x, torch.tensor([1.5, 1.5]).cuda())
+    assert torch.equal(ya, yb)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yc = ddpm.model(x, torch.tensor([1.5, 1.5]).cuda())   # selects the bf16 engine
+    assert rel_l2(yc, yb) < 3e-2 and not torch.equal(yc, yb)
+
+
+def test_errors():
+    import r2dm_b200 as R
+    cfg = SMALL_CFG
+    sd = O.random_state_dict(cfg, 3)
+    ddpm = make_ddpm(cfg, sd)
+    with pytest.raises(ValueError):
+        ddpm.model(torch.randn(1, 2, 8, 1024).cuda(), torch.zeros(1).cuda())
+    cpu = R.build_model(R.Config())
+    with pytest.raises(R._lib.R2dmError):
+        cpu.model(torch.randn(1, 2, 64, 1024), torch.zeros(1))
+    with pytest.raises(NotImplementedError):
+        ddpm(torch.randn(1, 2, 16, 1024).cuda())
