@@ -79,6 +79,12 @@ int r2dm_cond_embed(r2dm_handle h, const float* cond, int rows, float* scratch, 
 int r2dm_unet_forward(r2dm_handle h, const float* x, const float* film, const int* step_ptr,
                       int rows_per_step, int row_batch_stride, float* pred, void* stream);
 int r2dm_num_launches(r2dm_handle h); /* kernels enqueued by one r2dm_unet_forward */
+/* Measurement aid (bench.py): one eager forward with a CUDA-event pair around every launch; this
+ * call SYNCHRONISES and is never used on the product path.  Host arrays of capacity `cap` receive
+ * per launch: kind (0 pack_input, 1 conv3x3, 2 conv1x1, 3 GroupNorm/AdaGN apply, 4 down2, 5 up2,
+ * 6 attention), device milliseconds, algorithmic FLOPs and algorithmic bytes.  Returns #launches. */
+int r2dm_profile_forward(r2dm_handle h, const float* x, const float* film, float* pred, void* stream,
+                         int cap, int* kind, float* ms, double* flops, double* bytes);
 
 /* --- sampler step arithmetic (models/diffusion/continuous_time.py:208-229, 296-299;
  *     discrete_time.py:140-179).  coef rows: {ux, up, kx, k0, kn [, qa, qs]}:

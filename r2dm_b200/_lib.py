@@ -57,6 +57,8 @@ _SIGS = {
     "r2dm_cond_embed": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "r2dm_unet_forward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "r2dm_num_launches": (C.c_int, [_P]),
+    "r2dm_profile_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "r2dm_sampler_update": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_float,
                                       _P, _P, _P, C.c_int, C.c_size_t, _P]),
     "r2dm_axpby": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_size_t, _P]),

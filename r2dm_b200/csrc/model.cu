@@ -601,40 +601,100 @@ int r2dm_cond_embed(r2dm_handle h, const float* cond, int rows, float* scratch, 
   return 0;
 }
 
+static int launch_op(r2dm_handle h, Op& op, const float* x, const float* film, const int* step_ptr,
+                     int rows_per_step, int row_batch_stride, float* pred, cudaStream_t s) {
+  const r2dm_config& c = h->cfg;
+  switch (op.kind) {
+    case Op::PACK_INPUT: {
+      // rewrite only the planes that contain image channels; the rest is constant
+      const int pe = (c.in_channels + h->cw - 1) / h->cw;
+      CUDA_TRY(pack_input(h->dtype, x, c.in_channels, h->raw_enc >= 0 ? h->raw_ptr(h->raw_enc) : nullptr,
+                          c.extra_channels, op.a, 0, pe, s));
+      break;
+    }
+    case Op::CONV: {
+      if (op.is_output) op.conv.out_nchw = pred;
+      CUDA_TRY(conv_launch(op.conv, s));
+      break;
+    }
+    case Op::GN: {
+      if (op.gn_gamma < 0) {
+        op.gn.film = film; op.gn.step_ptr = step_ptr;
+        op.gn.rows_per_step = rows_per_step; op.gn.row_batch_stride = row_batch_stride;
+      }
+      CUDA_TRY(gn_apply_launch(op.gn, s));
+      break;
+    }
+    case Op::DOWN: CUDA_TRY(down2_launch(h->dtype, op.a, op.b, s)); break;
+    case Op::UP: CUDA_TRY(up2_launch(h->dtype, op.a, op.b, s)); break;
+    case Op::ATTN: CUDA_TRY(attention_launch(h->dtype, op.a, op.b, op.heads, s)); break;
+  }
+  return 0;
+}
+
 int r2dm_unet_forward(r2dm_handle h, const float* x, const float* film, const int* step_ptr, int rows_per_step,
                       int row_batch_stride, float* pred, void* stream) {
   if (!h || !x || !film || !pred) return fail(-1, "null argument");
   if (!h->ws) return fail(-1, "bind a workspace first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const r2dm_config& c = h->cfg;
   for (Op& op : h->prog) {
-    switch (op.kind) {
-      case Op::PACK_INPUT: {
-        // rewrite only the planes that contain image channels; the rest is constant
-        const int pe = (c.in_channels + h->cw - 1) / h->cw;
-        CUDA_TRY(pack_input(h->dtype, x, c.in_channels, h->raw_enc >= 0 ? h->raw_ptr(h->raw_enc) : nullptr,
-                            c.extra_channels, op.a, 0, pe, s));
-        break;
-      }
-      case Op::CONV: {
-        if (op.is_output) op.conv.out_nchw = pred;
-        CUDA_TRY(conv_launch(op.conv, s));
-        break;
-      }
-      case Op::GN: {
-        if (op.gn_gamma < 0) {
-          op.gn.film = film; op.gn.step_ptr = step_ptr;
-          op.gn.rows_per_step = rows_per_step; op.gn.row_batch_stride = row_batch_stride;
-        }
-        CUDA_TRY(gn_apply_launch(op.gn, s));
-        break;
-      }
-      case Op::DOWN: CUDA_TRY(down2_launch(h->dtype, op.a, op.b, s)); break;
-      case Op::UP: CUDA_TRY(up2_launch(h->dtype, op.a, op.b, s)); break;
-      case Op::ATTN: CUDA_TRY(attention_launch(h->dtype, op.a, op.b, op.heads, s)); break;
-    }
+    int rc = launch_op(h, op, x, film, step_ptr, rows_per_step, row_batch_stride, pred, s);
+    if (rc) return rc;
   }
   return 0;
+}
+
+// Measurement aid (bench.py / profiles): one eager forward with a CUDA event pair around every
+// launch.  Synchronises; never used on the product path.  kind: 0 pack_input, 1 conv3x3, 2 conv1x1,
+// 3 GroupNorm/AdaGN apply, 4 down2, 5 up2, 6 attention.  flops / bytes are ALGORITHMIC (unpadded).
+int r2dm_profile_forward(r2dm_handle h, const float* x, const float* film, float* pred, void* stream,
+                         int cap, int* kind, float* ms, double* flops, double* bytes) {
+  if (!h || !x || !film || !pred) return fail(-1, "null argument");
+  if (!h->ws) return fail(-1, "bind a workspace first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n = static_cast<int>(h->prog.size());
+  if (cap < n) return fail(-1, "capacity %d < %d ops", cap, n);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+  const double es = dtype_size(h->dtype);
+  for (int i = 0; i < n; ++i) {
+    Op& op = h->prog[i];
+    CUDA_TRY(cudaEventRecord(ev[i], s));
+    int rc = launch_op(h, op, x, film, nullptr, 0, 1, pred, s);
+    if (rc) return rc;
+    double fl = 0, by = 0;
+    int k = 0;
+    auto tb = [&](const PT& t) { return static_cast<double>(t.B) * t.C * t.H * t.W * es; };
+    switch (op.kind) {
+      case Op::PACK_INPUT: k = 0; by = static_cast<double>(op.a.B) * h->cfg.in_channels * op.a.H * op.a.W * 4 +
+                                      static_cast<double>(op.a.B) * h->cw * op.a.H * op.a.W * es; break;
+      case Op::CONV: {
+        const ConvW& w = h->convs[op.conv_w];
+        const PT& o = op.conv.out;
+        k = w.taps == 9 ? 1 : 2;
+        fl = 2.0 * o.B * o.H * o.W * w.cin * w.cout * w.taps;
+        by = static_cast<double>(o.B) * o.H * o.W * (w.cin * es + w.cout * (op.is_output ? 4.0 : es)) +
+             static_cast<double>(w.cin) * w.cout * w.taps * es + (op.conv.residual ? static_cast<double>(o.B) * o.H * o.W * w.cout * es : 0.0);
+        break;
+      }
+      case Op::GN: k = 3; by = 2.0 * tb(op.gn.dst); fl = 8.0 * op.gn.dst.B * op.gn.dst.C * op.gn.dst.H * op.gn.dst.W; break;
+      case Op::DOWN: k = 4; by = tb(op.a) + tb(op.b); break;
+      case Op::UP: k = 5; by = tb(op.a) + tb(op.b); break;
+      case Op::ATTN: {
+        k = 6;
+        const double Lt = static_cast<double>(op.b.H) * op.b.W;
+        fl = 4.0 * op.b.B * Lt * Lt * op.b.C;
+        by = tb(op.a) + tb(op.b);
+        break;
+      }
+    }
+    kind[i] = k; flops[i] = fl; bytes[i] = by;
+  }
+  CUDA_TRY(cudaEventRecord(ev[n], s));
+  CUDA_TRY(cudaEventSynchronize(ev[n]));
+  for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return n;
 }
 
 int r2dm_sampler_update(float* x_out, const float* x, const float* pred, const float* noise, const float* coef,

@@ -352,6 +352,23 @@ class UNetEngine:
             self.forward_film(x, film, pred)
         return pred
 
+    KINDS = ("pack_input", "conv3x3", "conv1x1", "gn_apply", "down2", "up2", "attention")
+
+    def profile_forward(self, x: torch.Tensor, cond: torch.Tensor):
+        """Measurement aid: per-launch (kind, ms, algorithmic flops, algorithmic bytes) of one eager
+        forward, timed with CUDA events on the launching stream.  Synchronises."""
+        x = L.f32c(x)
+        with torch.cuda.device(self.device):
+            film = self.cond_embed(cond)
+            pred = torch.empty_like(x)
+            self.bind(x.shape[0])
+            cap = self.launches_per_forward
+            kind, ms = (C.c_int * cap)(), (C.c_float * cap)()
+            fl, by = (C.c_double * cap)(), (C.c_double * cap)()
+            n = L.check(self.lib.r2dm_profile_forward(self.h, L.ptr(x), L.ptr(film), L.ptr(pred), L.stream_ptr(),
+                                                      cap, kind, ms, fl, by), "r2dm_profile_forward")
+        return [(self.KINDS[kind[i]], ms[i], fl[i], by[i]) for i in range(n)]
+
     def debug_tensor(self, name: str) -> torch.Tensor:
         """fp32 NCHW copy of a named intermediate of the last forward (needs R2DM_KEEP_ACTIVATIONS=1)."""
         c, hh, ww = C.c_int(), C.c_int(), C.c_int()
