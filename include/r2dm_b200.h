@@ -114,6 +114,11 @@ size_t r2dm_op_scratch_bytes(int batch, int max_channels, int H, int W);
 int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const float* bias,
                  const float* residual, float scale, float* y, int B, int Cin, int Cout, int H, int W,
                  void* scratch, size_t scratch_bytes, void* stream);
+/* the fused form the network actually runs: y = conv(act(GN(x))) + bias, GroupNorm/AdaGN(+SiLU) applied
+ * to the operand tile inside the conv kernel.  film: [B][2*Cin] = [scale || shift] (AdaGN) or NULL. */
+int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, const float* beta,
+                    const float* film, float eps, int silu, const float* w, const float* bias, float* y,
+                    int B, int Cin, int Cout, int H, int W, void* scratch, size_t scratch_bytes, void* stream);
 /* GroupNorm(8 groups) [+ FiLM: y = gn(x)*(1+fs)+fb when film_scale != NULL, per sample [B][C]] [+ SiLU] */
 int r2dm_op_groupnorm(int dtype, const float* x, const float* gamma, const float* beta,
                       const float* film_scale_shift, float eps, int silu, float* y, int B, int C, int H,

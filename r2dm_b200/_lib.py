@@ -68,6 +68,8 @@ _SIGS = {
     "r2dm_op_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "r2dm_op_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "r2dm_op_gn_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "r2dm_op_groupnorm": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, C.c_int,
                                     C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "r2dm_op_resample": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P,

@@ -1,32 +1,56 @@
-// Ring 3x3 / 1x1 convolution as an implicit GEMM on tcgen05 tensor cores (sm_100a).
+// Ring 3x3 / 1x1 convolution as an implicit GEMM on tcgen05 tensor cores (sm_100a), with the
+// preceding GroupNorm / AdaGN (+SiLU) fused into the operand path.
 //
 // Replaces, on the sampling path, models/ops.py:149-173 (Conv2d + Pad: circular azimuth padding,
 // zero elevation padding, 3x3 cross-correlation + bias), the 1x1 skip convolution of
-// models/efficient_unet.py:87-91 and the nn.MultiheadAttention in/out projections (:34-38).
+// models/efficient_unet.py:87-91, the nn.MultiheadAttention in/out projections (:34-38), and the
+// nn.GroupNorm / ops.AdaGN + nn.SiLU that feed them (efficient_unet.py:72-81,99-106; ops.py:176-200).
 //
-// One CTA computes an output tile of HT rows x 128 pixels x NT output channels:
-//   * warp 0   : producer.  Per pipeline stage (KCH input channels) one 5-D TMA box load brings the
-//                halo tile [(HT+2) x 130 px] of those channels into shared memory (planar-16
-//                layout, see common.cuh) and one bulk copy brings the pre-packed weights of all
-//                taps for those channels.
-//   * warp 1   : MMA issuer.  For every output row and every tap it issues tcgen05.mma with the A
-//                descriptor pointing at the *shifted* start address inside the halo tile, so the
-//                input is read from L2 once per tile instead of once per tap.  Accumulators for
-//                the HT rows live in TMEM (HT x NT fp32 columns).
-//   * warp 2   : TMEM allocator.
-//   * warps 4-7: epilogue.  tcgen05.ld -> + bias (+ residual) -> * scale -> GroupNorm partial
-//                sums for the consumer -> bf16/fp32 planar-16 store (incl. the wrap halo columns),
-//                or fp32 NCHW store for the network output.
+// Persistent kernel: one CTA per SM walks a contiguous range of output tiles (HT rows x 128 pixels
+// x NT output channels).  Warp roles (512 threads):
+//   warp 0      producer.  Per pipeline stage (KCH input channels) one 5-D TMA box load brings the
+//               halo tile [(HT+2) x 130 px] of those channels into shared memory (planar-16 layout,
+//               common.cuh) and one bulk copy brings the pre-packed weights of all taps for those
+//               channels - or, when the whole filter bank fits (Cin = Cout = 64), the weights are
+//               loaded once and stay resident.  The producer runs ahead across tile boundaries.
+//   warp 1      MMA issuer.  For every output row and tap one tcgen05.mma whose A descriptor points
+//               at the *shifted* start address inside the halo tile (so the input is read from L2
+//               once per tile, not once per tap).  Accumulators: 2 x (HT x NT) fp32 TMEM columns,
+//               double buffered so the epilogue of tile j overlaps the MMAs of tile j+1.
+//   warp 2      TMEM allocator.
+//   warps 4-7   operand transform (optional).  Applies y = silu(a_c x + d_c) in place on the freshly
+//               landed stage, where (a_c, d_c) fold the GroupNorm statistics left by the producer
+//               kernel, the affine / FiLM parameters and the normalisation; rows outside the image
+//               stay zero (the conv's zero padding applies to the *normalised* tensor).
+//   warps 8-15  epilogue.  tcgen05.ld -> + bias (+ residual) -> * scale -> GroupNorm partial sums
+//               for the consumer -> bf16/fp32 planar-16 store (incl. the wrap halo columns), or fp32
+//               NCHW store for the network output.
 // Elevation borders come from TMA out-of-bounds zero fill; the azimuth wrap from the halo columns.
 #include <cstdio>
+#include <cstring>
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
 namespace r2dm {
 
+constexpr int kMaxStages = 8;
+constexpr int kMaxCin = 1024;
+
+struct XformParams {
+  int enabled, silu;
+  const float* stats0; const float* stats1;   // partial (sum, sumsq) of the source tensor(s)
+  int C0, C1, slots0, slots1;
+  const float* gamma; const float* beta;      // affine GroupNorm, or
+  const float* film;                          // AdaGN table (scale at film_off, shift at +Ctot)
+  int film_stride, film_off;
+  const int* step_ptr; int rows_per_step, row_batch_stride;
+  int groups; float eps;
+};
+
 struct ConvParams {
   CUtensorMap tmap0, tmap1;
+  XformParams xf;
   const void* wpacked;
   const float* bias;
   const void* residual;
@@ -36,13 +60,14 @@ struct ConvParams {
   int B, H, W;
   int cout, cout_pad;     // real / padded output channels
   int nk, ksplit;         // pipeline stages over K; first stage that reads from tmap1
-  int xtiles, ytiles, ntiles;
+  int xtiles, ytiles, ntiles, tiles_total;
   int unit_ch;            // output channels per statistics unit (cout / kNU)
   int slots;
   float scale;
+  int stages, stage_bytes, wres;  // smem ring depth / stride; weights resident in smem
 };
 
-template <typename T, int NT, int HT, int TAPS, int KS, int STAGES>
+template <typename T, int NT, int HT, int TAPS, int KS>
 struct ConvTraits {
   static constexpr int CW = Elem<T>::CW;
   static constexpr int KCH = KS * 2 * CW;
@@ -55,38 +80,45 @@ struct ConvTraits {
   static constexpr int B_PLANE_BYTES = NT * 16;
   static constexpr int B_TAP_BYTES = PLANES * B_PLANE_BYTES;
   static constexpr int B_BYTES = TAPS * B_TAP_BYTES;
-  static constexpr int STAGE_BYTES = A_BYTES_AL + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
   static constexpr int ACC_COLS = HT * NT;
-  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128
-                                   : ACC_COLS <= 256 ? 256 : 512;
-  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
+                                   : 2 * ACC_COLS <= 256 ? 256 : 512;
+  static_assert(2 * ACC_COLS <= 512, "double-buffered accumulators exceed TMEM");
   static_assert(B_BYTES % 128 == 0, "weight stage must stay 128B aligned");
 };
 
-template <typename T, int NT, int HT, int TAPS, int KS, int STAGES, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+__device__ __forceinline__ float silu_fast(float t) {  // 0.5 t (1 + tanh(t/2)), one MUFU op
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * t));
+  return 0.5f * t * (1.f + th);
+}
+
+template <typename T, int NT, int HT, int TAPS, int KS>
+__global__ void __launch_bounds__(512, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
-  using Tr = ConvTraits<T, NT, HT, TAPS, KS, STAGES>;
+  using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
   constexpr int CW = Tr::CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], xf_bar[kMaxStages];
+  __shared__ uint64_t acc_full[2], acc_empty[2], wres_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float bias_s[NT];
-  __shared__ float stat_s[4][kNU][2];
+  __shared__ float stat_s[2][8][kNU][2];
+  __shared__ float coef_s[2][kMaxCin];
+  __shared__ float grp_s[2][kNU];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int bid = blockIdx.x;
-  const int nt = bid % p.ntiles; bid /= p.ntiles;
-  const int xt = bid % p.xtiles; bid /= p.xtiles;
-  const int yt = bid % p.ytiles;
-  const int b = bid / p.ytiles;
-  const int n0 = nt * NT, x0 = xt * 128, y0 = yt * HT;
+  const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.tiles_total / gridDim.x);
+  const int t_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.tiles_total / gridDim.x);
+  const uint32_t wres_bytes = p.wres ? static_cast<uint32_t>(p.nk) * Tr::B_BYTES : 0u;
+  uint8_t* smem_w = smem;                 // resident weights (if any)
+  uint8_t* smem_ring = smem + wres_bytes; // stage ring
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&xf_bar[i], 4); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
+    mbar_init(&wres_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tmap0);
     if (p.ksplit < p.nk) tma_prefetch_desc(&p.tmap1);
@@ -97,143 +129,306 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
+  auto decode = [&](int t, int& b, int& yt, int& xt, int& nt) {
+    nt = t % p.ntiles; t /= p.ntiles;
+    xt = t % p.xtiles; t /= p.xtiles;
+    yt = t % p.ytiles;
+    b = t / p.ytiles;
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
-      const uint8_t* wsrc = static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(nt) * p.nk * Tr::B_BYTES;
-      for (int ks = 0; ks < p.nk; ++ks) {
-        const int st = ks % STAGES;
-        const uint32_t ph = (ks / STAGES) & 1;
-        mbar_wait(&empty_bar[st], ph ^ 1);
-        uint8_t* sa = smem + st * Tr::STAGE_BYTES;
-        uint8_t* sb = sa + Tr::A_BYTES_AL;
-        mbar_expect_tx(&full_bar[st], Tr::A_BYTES + Tr::B_BYTES);
-        const bool second = ks >= p.ksplit;
-        const int plane0 = (second ? ks - p.ksplit : ks) * Tr::PLANES;
-        const CUtensorMap* tm = second ? &p.tmap1 : &p.tmap0;
-        if (TAPS == 9) tma_load_5d(sa, tm, &full_bar[st], 0, x0, y0 - 1, plane0, b);
-        else tma_load_5d(sa, tm, &full_bar[st], 0, x0 + 1, y0, plane0, b);
-        bulk_load(sb, wsrc + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES, &full_bar[st]);
+      if (p.wres) {
+        mbar_expect_tx(&wres_bar, wres_bytes);
+        for (int ks = 0; ks < p.nk; ++ks)
+          bulk_load(smem_w + static_cast<size_t>(ks) * Tr::B_BYTES,
+                    static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES,
+                    &wres_bar);
+      }
+      uint32_t it = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        int b, yt, xt, nt;
+        decode(t, b, yt, xt, nt);
+        const int x0 = xt * 128, y0 = yt * HT;
+        const uint8_t* wsrc = static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(nt) * p.nk * Tr::B_BYTES;
+        for (int ks = 0; ks < p.nk; ++ks, ++it) {
+          const int st = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          uint8_t* sa = smem_ring + static_cast<size_t>(st) * p.stage_bytes;
+          mbar_expect_tx(&full_bar[st], Tr::A_BYTES + (p.wres ? 0 : Tr::B_BYTES));
+          const bool second = ks >= p.ksplit;
+          const int plane0 = (second ? ks - p.ksplit : ks) * Tr::PLANES;
+          const CUtensorMap* tm = second ? &p.tmap1 : &p.tmap0;
+          if (TAPS == 9) tma_load_5d(sa, tm, &full_bar[st], 0, x0, y0 - 1, plane0, b);
+          else tma_load_5d(sa, tm, &full_bar[st], 0, x0 + 1, y0, plane0, b);
+          if (!p.wres)
+            bulk_load(sa + Tr::A_BYTES_AL, wsrc + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES, &full_bar[st]);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, NT, Elem<T>::kFmt);
-      // descriptor halves: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 | version<<14 | layout<<29
+      // descriptor halves: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 | version<<14 (no swizzle)
       const uint32_t a_lo_const = static_cast<uint32_t>(Tr::A_PLANE_BYTES >> 4) << 16;
       const uint32_t b_lo_const = static_cast<uint32_t>(Tr::B_PLANE_BYTES >> 4) << 16;
       const uint32_t hi = (128u >> 4) | (1u << 14);
-      for (int ks = 0; ks < p.nk; ++ks) {
-        const int st = ks % STAGES;
-        const uint32_t ph = (ks / STAGES) & 1;
-        mbar_wait(&full_bar[st], ph);
+      if (p.wres) mbar_wait(&wres_bar, 0);
+      uint32_t it = 0;
+      int j = 0;
+      for (int t = t_begin; t < t_end; ++t, ++j) {
+        const int buf = j & 1;
+        mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + st * Tr::STAGE_BYTES);
-        const uint32_t sb = sa + Tr::A_BYTES_AL;
+        const uint32_t dbase = tmem + buf * Tr::ACC_COLS;
+        for (int ks = 0; ks < p.nk; ++ks, ++it) {
+          const int st = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(p.xf.enabled ? &xf_bar[st] : &full_bar[st], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_ring + static_cast<size_t>(st) * p.stage_bytes);
+          const uint32_t sb = p.wres ? smem_u32(smem_w) + static_cast<uint32_t>(ks) * Tr::B_BYTES : sa + Tr::A_BYTES_AL;
 #pragma unroll
-        for (int r = 0; r < HT; ++r) {
+          for (int r = 0; r < HT; ++r) {
 #pragma unroll
-          for (int tap = 0; tap < TAPS; ++tap) {
-            const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
-            const uint32_t a_off = static_cast<uint32_t>(((r + dy) * Tr::APITCH + dx) * 16);
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
+              const uint32_t a_off = static_cast<uint32_t>(((r + dy) * Tr::APITCH + dx) * 16);
 #pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
-              const uint32_t aa = sa + kk * 2 * Tr::A_PLANE_BYTES + a_off;
-              const uint32_t ba = sb + tap * Tr::B_TAP_BYTES + kk * 2 * Tr::B_PLANE_BYTES;
-              const uint64_t adesc = (static_cast<uint64_t>(hi) << 32) | (a_lo_const | ((aa >> 4) & 0x3FFFu));
-              const uint64_t bdesc = (static_cast<uint64_t>(hi) << 32) | (b_lo_const | ((ba >> 4) & 0x3FFFu));
-              const uint32_t acc = (ks > 0 || tap > 0 || kk > 0) ? 1u : 0u;
-              if (Elem<T>::kFmt == 2) umma_tf32(tmem + r * NT, adesc, bdesc, idesc, acc);
-              else umma_f16(tmem + r * NT, adesc, bdesc, idesc, acc);
+              for (int kk = 0; kk < KS; ++kk) {
+                const uint32_t aa = sa + kk * 2 * Tr::A_PLANE_BYTES + a_off;
+                const uint32_t ba = sb + tap * Tr::B_TAP_BYTES + kk * 2 * Tr::B_PLANE_BYTES;
+                const uint64_t adesc = (static_cast<uint64_t>(hi) << 32) | (a_lo_const | ((aa >> 4) & 0x3FFFu));
+                const uint64_t bdesc = (static_cast<uint64_t>(hi) << 32) | (b_lo_const | ((ba >> 4) & 0x3FFFu));
+                const uint32_t acc = (ks > 0 || tap > 0 || kk > 0) ? 1u : 0u;
+                if (Elem<T>::kFmt == 2) umma_tf32(dbase + r * NT, adesc, bdesc, idesc, acc);
+                else umma_f16(dbase + r * NT, adesc, bdesc, idesc, acc);
+              }
             }
           }
+          umma_commit(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
         }
-        umma_commit(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
+        umma_commit(&acc_full[buf]);
       }
-      umma_commit(&accum_bar);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ operand transform
+    if (p.xf.enabled) {
+      const int tt = threadIdx.x - 128;                 // 0..127
+      constexpr int TPP = 128 / Tr::PLANES;             // threads per channel plane
+      const int my_plane = tt / TPP, tip = tt % TPP;
+      const int Ctot = p.xf.C0 + p.xf.C1;
+      const int gsize = Ctot / p.xf.groups;
+      uint32_t it = 0;
+      int cur_b = -1;
+      for (int t = t_begin; t < t_end; ++t) {
+        int b, yt, xt, nt;
+        decode(t, b, yt, xt, nt);
+        if (b != cur_b) {
+          // ---- fold statistics + affine/FiLM into per-channel (a, d) for image b
+          cur_b = b;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          {
+            const int g = tt >> 4, l16 = tt & 15;        // 16 threads per group (groups == 8)
+            double s1 = 0.0, s2 = 0.0;
+            const int lo = g * gsize, hi_c = lo + gsize;
+            int off = 0;
+            for (int si = 0; si < 2; ++si) {
+              const int Cs = si == 0 ? p.xf.C0 : p.xf.C1;
+              if (Cs == 0) break;
+              const float* stp = si == 0 ? p.xf.stats0 : p.xf.stats1;
+              const int sl = si == 0 ? p.xf.slots0 : p.xf.slots1;
+              const int a = max(lo, off), e = min(hi_c, off + Cs);
+              if (a < e) {
+                const int unit_ch = Cs / kNU;
+                const int u0 = (a - off) / unit_ch, u1 = (e - off) / unit_ch;
+                const int n = (u1 - u0) * sl;
+                const float* st = stp + (static_cast<size_t>(b) * kNU + u0) * sl * 2;
+                for (int i = l16; i < n; i += 16) { s1 += st[2 * i]; s2 += st[2 * i + 1]; }
+              }
+              off += Cs;
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (l16 == 0) {
+              const double cnt = static_cast<double>(gsize) * p.H * p.W;
+              const double mean = s1 / cnt;
+              double var = s2 / cnt - mean * mean;
+              if (var < 0.0) var = 0.0;
+              grp_s[0][g] = static_cast<float>(mean);
+              grp_s[1][g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.xf.eps)));
+            }
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const float* fl = nullptr;
+          if (p.xf.film != nullptr) {
+            const int row = (p.xf.step_ptr ? *p.xf.step_ptr : 0) * p.xf.rows_per_step + b * p.xf.row_batch_stride;
+            fl = p.xf.film + static_cast<size_t>(row) * p.xf.film_stride + p.xf.film_off;
+          }
+          for (int c = tt; c < Ctot; c += 128) {
+            const int g = c / gsize;
+            const float ga = fl ? 1.f + fl[c] : p.xf.gamma[c];
+            const float be = fl ? fl[Ctot + c] : p.xf.beta[c];
+            const float a = grp_s[1][g] * ga;
+            coef_s[0][c] = a;
+            coef_s[1][c] = be - grp_s[0][g] * a;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        const int y_first = TAPS == 9 ? yt * HT - 1 : yt * HT;   // image row of tile row 0
+        const int row_lo = max(0, -y_first), row_hi = min(Tr::AROWS, p.H - y_first);
+        const int n_units = (row_hi - row_lo) * Tr::APITCH;
+        for (int ks = 0; ks < p.nk; ++ks, ++it) {
+          const int st = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          float ca[CW], cd[CW];
+          const int c0 = (ks * Tr::PLANES + my_plane) * CW;
+#pragma unroll
+          for (int i = 0; i < CW; ++i) {
+            const bool ok = c0 + i < Ctot;
+            ca[i] = ok ? coef_s[0][c0 + i] : 0.f;
+            cd[i] = ok ? coef_s[1][c0 + i] : 0.f;
+          }
+          mbar_wait(&full_bar[st], ph);
+          uint4* base = reinterpret_cast<uint4*>(smem_ring + static_cast<size_t>(st) * p.stage_bytes +
+                                                 my_plane * Tr::A_PLANE_BYTES) + row_lo * Tr::APITCH;
+          if (c0 < Ctot) {
+#pragma unroll 4
+            for (int i = tip; i < n_units; i += TPP) {
+              float v[CW];
+              Elem<T>::unpack(base[i], v);
+#pragma unroll
+              for (int k = 0; k < CW; ++k) {
+                const float tv = fmaf(v[k], ca[k], cd[k]);
+                v[k] = p.xf.silu ? (sizeof(T) == 2 ? silu_fast(tv) : silu_f(tv)) : tv;
+              }
+              base[i] = Elem<T>::pack_mma(v);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xf_bar[st]);
+        }
+      }
+    }
+  } else if (warp >= 8) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;
-    const int m = ew * 32 + lane;
-    const int x = x0 + m;
-    for (int i = m; i < NT; i += 128) bias_s[i] = p.bias[n0 + i];
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int ew = warp - 8;            // 0..7
+    const int q = ew & 3;               // TMEM lane quarter (must equal warp % 4)
+    const int half = ew >> 2;           // which rows (HT > 1) or which column half (HT == 1)
+    const int m = q * 32 + lane;
     const int Wp = p.W + 2;
     const int planes_out = p.cout_pad / CW;
     constexpr int NUT = NT >= 8 * kNU ? kNU : (NT / 8 > 0 ? NT / 8 : 1);  // max units per tile
-    float sacc[NUT][2];
-#pragma unroll
-    for (int u = 0; u < NUT; ++u) { sacc[u][0] = 0.f; sacc[u][1] = 0.f; }
+    constexpr int CB = NT >= 32 ? 32 : 16;   // columns per TMEM load batch
     const uint4* res = static_cast<const uint4*>(p.residual);
     uint4* out = static_cast<uint4*>(p.out);
-
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
+    const int ethread = threadIdx.x - 256;
+    int j = 0;
+    for (int t = t_begin; t < t_end; ++t, ++j) {
+      int b, yt, xt, nt;
+      decode(t, b, yt, xt, nt);
+      const int n0 = nt * NT, x = xt * 128 + m, y0 = yt * HT;
+      const int buf = j & 1;
+      float sacc[NUT][2];
+#pragma unroll
+      for (int u = 0; u < NUT; ++u) { sacc[u][0] = 0.f; sacc[u][1] = 0.f; }
+      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem + buf * Tr::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      constexpr int RSTEP = HT > 1 ? 2 : 1;
+      const int r_begin = HT > 1 ? half : 0;
+      const int c_begin = HT > 1 ? 0 : half * (NT / 2);
+      const int c_end = HT > 1 ? NT : c_begin + NT / 2;
 #pragma unroll 1
-    for (int r = 0; r < HT; ++r) {
-      const int y = y0 + r;
-      if (y >= p.H) break;
+      for (int r = r_begin; r < HT; r += RSTEP) {
+        const int y = y0 + r;
+        if (y >= p.H) break;
 #pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem + (static_cast<uint32_t>(ew * 32) << 16) + r * NT + c0, v);
-        tmem_ld_wait();
-        if (p.out_nchw != nullptr) {
+        for (int c0 = c_begin; c0 < c_end; c0 += CB) {
+          // residual prefetch (independent loads in flight while TMEM is read)
+          uint4 rr[CB / CW];
+          if (res != nullptr && p.out_nchw == nullptr) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int ch = n0 + c0 + i;
-            if (ch < p.cout)
-              p.out_nchw[((static_cast<size_t>(b) * p.cout + ch) * p.H + y) * p.W + x] =
-                  (v[i] + bias_s[c0 + i]) * p.scale;
+            for (int u = 0; u < CB / CW; ++u)
+              rr[u] = res[pt_index(b, planes_out, (n0 + c0) / CW + u, p.H, Wp, y, x + 1)];
           }
-          continue;
-        }
+          float v[CB];
 #pragma unroll
-        for (int u = 0; u < 16 / CW; ++u) {
-          const int cl = c0 + u * CW;  // channel within the N tile
-          const int plane = (n0 + cl) / CW;
-          const size_t idx = pt_index(b, planes_out, plane, p.H, Wp, y, x + 1);
-          float o[CW];
+          for (int h16 = 0; h16 < CB / 16; ++h16) tmem_ld16(tbase + r * NT + c0 + h16 * 16, v + h16 * 16);
+          tmem_ld_wait();
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
 #pragma unroll
-          for (int i = 0; i < CW; ++i) o[i] = v[u * CW + i] + bias_s[cl + i];
-          if (res != nullptr) {
-            float rv[CW];
-            Elem<T>::unpack(res[idx], rv);
-#pragma unroll
-            for (int i = 0; i < CW; ++i) o[i] += rv[i];
+          for (int i4 = 0; i4 < CB / 4; ++i4) {
+            const float4 bv = __ldg(bias4 + i4);
+            v[4 * i4] += bv.x; v[4 * i4 + 1] += bv.y; v[4 * i4 + 2] += bv.z; v[4 * i4 + 3] += bv.w;
           }
-          float s1 = 0.f, s2 = 0.f;
+          if (p.out_nchw != nullptr) {
 #pragma unroll
-          for (int i = 0; i < CW; ++i) { o[i] *= p.scale; s1 += o[i]; s2 += o[i] * o[i]; }
-          if (p.stats != nullptr) {
-            const int un = cl / p.unit_ch;
-#pragma unroll
-            for (int q = 0; q < NUT; ++q)
-              if (q == un) { sacc[q][0] += s1; sacc[q][1] += s2; }
+            for (int i = 0; i < CB; ++i) {
+              const int ch = n0 + c0 + i;
+              if (ch < p.cout)
+                p.out_nchw[((static_cast<size_t>(b) * p.cout + ch) * p.H + y) * p.W + x] = v[i] * p.scale;
+            }
+            continue;
           }
-          const uint4 pk = Elem<T>::pack(o);
-          out[idx] = pk;
-          if (x == 0) out[idx + p.W] = pk;              // xp = W+1 mirrors pixel 0
-          if (x == p.W - 1) out[idx - p.W] = pk;        // xp = 0 mirrors pixel W-1
+#pragma unroll
+          for (int u = 0; u < CB / CW; ++u) {
+            const int cl = c0 + u * CW;  // channel within the N tile
+            const size_t idx = pt_index(b, planes_out, (n0 + cl) / CW, p.H, Wp, y, x + 1);
+            float o[CW];
+#pragma unroll
+            for (int i = 0; i < CW; ++i) o[i] = v[u * CW + i];
+            if (res != nullptr) {
+              float rv[CW];
+              Elem<T>::unpack(rr[u], rv);
+#pragma unroll
+              for (int i = 0; i < CW; ++i) o[i] += rv[i];
+            }
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < CW; ++i) { o[i] *= p.scale; s1 += o[i]; s2 += o[i] * o[i]; }
+            if (p.stats != nullptr) {
+              const int un = cl / p.unit_ch;
+#pragma unroll
+              for (int qq = 0; qq < NUT; ++qq)
+                if (qq == un) { sacc[qq][0] += s1; sacc[qq][1] += s2; }
+            }
+            const uint4 pk = Elem<T>::pack(o);
+            out[idx] = pk;
+            if (x == 0) out[idx + p.W] = pk;              // xp = W+1 mirrors pixel 0
+            if (x == p.W - 1) out[idx - p.W] = pk;        // xp = 0 mirrors pixel W-1
+          }
         }
       }
-    }
-    if (p.stats != nullptr) {
+      // this warp is done with the TMEM buffer: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (p.stats != nullptr) {
+        const int par = j & 1;
 #pragma unroll
-      for (int u = 0; u < NUT; ++u) {
-        const float a = warp_sum(sacc[u][0]), q = warp_sum(sacc[u][1]);
-        if (lane == 0) { stat_s[ew][u][0] = a; stat_s[ew][u][1] = q; }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int units_here = NT / p.unit_ch;
-      if (m < units_here * 2) {
-        const int u = m >> 1, k = m & 1;
-        const float tot = stat_s[0][u][k] + stat_s[1][u][k] + stat_s[2][u][k] + stat_s[3][u][k];
-        const int unit = n0 / p.unit_ch + u;
-        const int slot = yt * p.xtiles + xt;
-        p.stats[((static_cast<size_t>(b) * kNU + unit) * p.slots + slot) * 2 + k] = tot;
+        for (int u = 0; u < NUT; ++u) {
+          const float a = warp_sum(sacc[u][0]), qv = warp_sum(sacc[u][1]);
+          if (lane == 0) { stat_s[par][ew][u][0] = a; stat_s[par][ew][u][1] = qv; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int units_here = NT / p.unit_ch;
+        if (ethread < units_here * 2) {
+          const int u = ethread >> 1, k = ethread & 1;
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) tot += stat_s[par][w][u][k];
+          const int unit = n0 / p.unit_ch + u;
+          const int slot = yt * p.xtiles + xt;
+          p.stats[((static_cast<size_t>(b) * kNU + unit) * p.slots + slot) * 2 + k] = tot;
+        }
       }
     }
   }
@@ -293,17 +488,31 @@ int conv_make_tmaps(ConvLaunch& l) {
   return rc;
 }
 
-template <typename T, int NT, int HT, int TAPS, int KS, int STAGES, int MINB>
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+constexpr int kSmemBudget = 216 * 1024;     // dynamic smem per CTA (227 KB limit minus ~9.5 KB static)
+constexpr int kWresMaxBytes = 80 * 1024;    // keep the filter bank resident below this size
+
+template <typename T, int NT, int HT, int TAPS, int KS>
 static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
-  using Tr = ConvTraits<T, NT, HT, TAPS, KS, STAGES>;
-  auto kern = conv_umma_kernel<T, NT, HT, TAPS, KS, STAGES, MINB>;
+  using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
+  auto kern = conv_umma_kernel<T, NT, HT, TAPS, KS>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tr::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   ConvParams p;
+  memset(&p, 0, sizeof(p));
   p.tmap0 = l.tmap0; p.tmap1 = l.tmap1;
   p.wpacked = l.wpacked; p.bias = l.bias; p.residual = l.residual;
   p.out = l.out.ptr; p.out_nchw = l.out_nchw; p.stats = l.out_nchw ? nullptr : l.out.stats;
@@ -312,27 +521,52 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.nk = l.cin_pad / Tr::KCH;
   p.ksplit = l.in1.ptr ? l.in0.C / Tr::KCH : p.nk;
   p.xtiles = l.out.W / 128; p.ytiles = (l.out.H + HT - 1) / HT; p.ntiles = l.cout_pad / NT;
+  p.tiles_total = p.B * p.ytiles * p.xtiles * p.ntiles;
   p.unit_ch = l.cout / kNU > 0 ? l.cout / kNU : 1;
   p.slots = l.out.slots;
   p.scale = l.scale;
-  const int grid = p.B * p.ytiles * p.xtiles * p.ntiles;
-  kern<<<grid, 256, Tr::SMEM_BYTES, s>>>(p);
+  // operand transform (fused GroupNorm / AdaGN + SiLU)
+  if (l.xf.enabled) {
+    XformParams& x = p.xf;
+    x.enabled = 1; x.silu = l.xf.silu;
+    x.stats0 = l.in0.stats; x.C0 = l.xf.c0_real > 0 ? l.xf.c0_real : l.in0.C; x.slots0 = l.in0.slots;
+    x.stats1 = l.in1.ptr ? l.in1.stats : nullptr; x.C1 = l.in1.ptr ? l.in1.C : 0; x.slots1 = l.in1.slots;
+    x.gamma = l.xf.gamma; x.beta = l.xf.beta; x.film = l.xf.film;
+    x.film_stride = l.xf.film_stride; x.film_off = l.xf.film_off;
+    x.step_ptr = l.xf.step_ptr; x.rows_per_step = l.xf.rows_per_step; x.row_batch_stride = l.xf.row_batch_stride;
+    x.groups = l.xf.groups; x.eps = l.xf.eps;
+    if (x.C0 + x.C1 > kMaxCin || x.stats0 == nullptr) return cudaErrorInvalidValue;
+  }
+  // shared-memory plan: resident weights when the whole bank of this N tile fits, then as many
+  // ring stages as the budget allows
+  const size_t wbytes = static_cast<size_t>(p.nk) * Tr::B_BYTES;
+  p.wres = (p.ntiles == 1 && wbytes <= static_cast<size_t>(kWresMaxBytes)) ? 1 : 0;
+  p.stage_bytes = Tr::A_BYTES_AL + (p.wres ? 0 : Tr::B_BYTES);
+  const int avail = kSmemBudget - 256 - (p.wres ? static_cast<int>(wbytes) : 0);
+  int stages = avail / p.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return cudaErrorInvalidConfiguration;
+  p.stages = stages;
+  const int smem = 256 + (p.wres ? static_cast<int>(wbytes) : 0) + stages * p.stage_bytes;
+  int grid = num_sms();
+  if (grid > p.tiles_total) grid = p.tiles_total;
+  kern<<<grid, 512, smem, s>>>(p);
   return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t dispatch(const ConvLaunch& l, cudaStream_t s) {
   if (l.taps == 9) {
-    if (l.nt == 64 && l.ht == 4) return launch_one<T, 64, 4, 9, 1, 2, 2>(l, s);
-    if (l.nt == 64 && l.ht == 2) return launch_one<T, 64, 2, 9, 1, 3, 2>(l, s);
-    if (l.nt == 128 && l.ht == 2) return launch_one<T, 128, 2, 9, 1, 2, 2>(l, s);
-    if (l.nt == 128 && l.ht == 1) return launch_one<T, 128, 1, 9, 1, 2, 2>(l, s);
-    if (l.nt == 16 && l.ht == 4) return launch_one<T, 16, 4, 9, 1, 3, 2>(l, s);
+    if (l.nt == 64 && l.ht == 4) return launch_one<T, 64, 4, 9, 1>(l, s);
+    if (l.nt == 64 && l.ht == 2) return launch_one<T, 64, 2, 9, 1>(l, s);
+    if (l.nt == 128 && l.ht == 2) return launch_one<T, 128, 2, 9, 1>(l, s);
+    if (l.nt == 128 && l.ht == 1) return launch_one<T, 128, 1, 9, 1>(l, s);
+    if (l.nt == 16 && l.ht == 4) return launch_one<T, 16, 4, 9, 1>(l, s);
   } else if (l.taps == 1) {
-    if (l.nt == 64 && l.ht == 2) return launch_one<T, 64, 2, 1, 4, 2, 2>(l, s);
-    if (l.nt == 128 && l.ht == 2) return launch_one<T, 128, 2, 1, 4, 2, 2>(l, s);
-    if (l.nt == 128 && l.ht == 1) return launch_one<T, 128, 1, 1, 4, 3, 2>(l, s);
-    if (l.nt == 64 && l.ht == 1) return launch_one<T, 64, 1, 1, 4, 3, 2>(l, s);
+    if (l.nt == 64 && l.ht == 2) return launch_one<T, 64, 2, 1, 4>(l, s);
+    if (l.nt == 128 && l.ht == 2) return launch_one<T, 128, 2, 1, 4>(l, s);
+    if (l.nt == 128 && l.ht == 1) return launch_one<T, 128, 1, 1, 4>(l, s);
+    if (l.nt == 64 && l.ht == 1) return launch_one<T, 64, 1, 1, 4>(l, s);
   }
   return cudaErrorInvalidConfiguration;
 }

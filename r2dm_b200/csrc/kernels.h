@@ -22,6 +22,20 @@ struct PT {
 };
 
 // ------------------------------------------------------------------ implicit-GEMM convolution
+// GroupNorm / AdaGN (+SiLU) applied to the conv input inside the conv kernel (statistics come from
+// in0.stats / in1.stats, i.e. from the kernel that produced the input tensors).
+struct ConvXform {
+  int enabled;
+  int silu;
+  int groups;
+  float eps;
+  const float* gamma; const float* beta;  // affine GN, or null for AdaGN
+  const float* film;                      // AdaGN table [rows][film_stride]; scale at film_off, shift at +C
+  int film_stride, film_off;
+  const int* step_ptr; int rows_per_step, row_batch_stride;
+  int c0_real;                            // real channel count of in0 if it is zero padded (0 = in0.C)
+};
+
 struct ConvLaunch {
   int dtype;          // kF32 (tf32 tensor cores) or kBF16
   int taps;           // 9 (3x3 ring conv) or 1 (1x1 conv / linear over tokens)
@@ -35,6 +49,7 @@ struct ConvLaunch {
   const void* residual;  // planar-16 tensor added before scaling, or null
   float scale;        // applied after bias (+ residual)
   float* out_nchw;    // if non-null: write fp32 [B][cout][H][W] instead of `out`
+  ConvXform xf;       // fused input normalisation (enabled = 0: plain convolution)
   CUtensorMap tmap0, tmap1;
 };
 // Fills l.tmap0/tmap1 for the current in0/in1 pointers.  Returns 0 on success.

@@ -61,6 +61,7 @@ struct Op {
   int conv_w = -1;        // index into convs (weights/bias resolved at bind)
   int gn_gamma = -1;      // raw index of gamma (beta = +1), or -1 for AdaGN
   bool is_output = false; // network output conv (writes pred NCHW)
+  bool xf_film = false;   // conv with fused AdaGN: film pointers patched per forward
 };
 
 }  // namespace
@@ -235,8 +236,10 @@ struct Builder {
 
   const PT& T(int id) const { return pl.tensors[id]; }
 
+  // xf: 0 none, 1 GroupNorm(affine from raw index gamma_raw)+SiLU, 2 AdaGN(film_name)+SiLU,
+  //     3 GroupNorm(affine) without SiLU (attention)
   int conv(const std::string& wname, int in0, int in1, int residual, float scale, bool want_stats,
-           bool is_output = false) {
+           bool is_output = false, int xf = 0, int gamma_raw = -1, const std::string& film_name = "") {
     const int wi = m->conv_by_name.at(wname);
     const ConvW& w = m->convs[wi];
     const PT& a = T(in0);
@@ -266,6 +269,19 @@ struct Builder {
       l.out.stats = nullptr; l.out.slots = 0;
     }
     l.residual = residual >= 0 ? T(residual).ptr : nullptr;
+    if (xf != 0) {
+      l.xf.enabled = 1;
+      l.xf.silu = xf != 3;
+      l.xf.groups = m->cfg.gn_num_groups;
+      l.xf.eps = m->cfg.gn_eps;
+      if (xf == 2) {
+        op.xf_film = true;
+        l.xf.film_off = m->film_rows.at(film_name).first;
+        l.xf.film_stride = m->F;
+      } else {
+        op.gn_gamma = gamma_raw;
+      }
+    }
     prog.push_back(op);
     return out_id;
   }
@@ -333,18 +349,15 @@ struct Builder {
       for (int i = 0; i < b.nres; ++i) {
         const std::string p = b.name + ".residual_blocks." + std::to_string(i);
         const int x0 = h, x1 = (i == 0) ? h2 : -1;
-        const int xn = gn(x0, x1, m->raw_by_name.at(p + ".norm1.weight"), "", true);
-        const int h1 = conv(p + ".conv1", xn, -1, -1, 1.f, true);
-        pl.release(xn);
-        const int hn = gn(h1, -1, -1, p + ".norm2.proj.1", true);
-        pl.release(h1);
+        // GroupNorm+SiLU and AdaGN+SiLU run inside the consumer convolutions (operand transform)
+        const int h1 = conv(p + ".conv1", x0, x1, -1, 1.f, true, false, 1, m->raw_by_name.at(p + ".norm1.weight"));
         int res = x0, sk = -1;
         if (m->conv_by_name.count(p + ".skip")) {
           sk = conv(p + ".skip", x0, x1, -1, 1.f, false);
           res = sk;
         }
-        const int o = conv(p + ".conv2", hn, -1, res, rs, true);
-        pl.release(hn);
+        const int o = conv(p + ".conv2", h1, -1, res, rs, true, false, 2, -1, p + ".norm2.proj.1");
+        pl.release(h1);
         if (sk >= 0) pl.release(sk);
         pl.release(x0);
         if (x1 >= 0) pl.release(x1);
@@ -353,9 +366,7 @@ struct Builder {
       }
       if (b.attn) {
         const std::string p = b.name + ".self_attn_block";
-        const int xn = gn(h, -1, m->raw_by_name.at(p + ".norm.weight"), "", false);
-        const int qkv = conv(p + ".attn.in_proj", xn, -1, -1, 1.f, false);
-        pl.release(xn);
+        const int qkv = conv(p + ".attn.in_proj", h, -1, -1, 1.f, false, false, 3, m->raw_by_name.at(p + ".norm.weight"));
         const int att = pl.new_tensor(b.cout, T(h).H, T(h).W, 0);
         {
           Op op; op.kind = Op::ATTN; op.a = T(qkv); op.b = T(att); op.heads = c.attn_num_heads;
@@ -567,6 +578,10 @@ int r2dm_bind_workspace(r2dm_handle h, void* workspace, size_t bytes, int batch,
       op.conv.bias = reinterpret_cast<const float*>(h->arena + w.b_off);
       int rc = conv_make_tmaps(op.conv);
       if (rc) return fail(-4, "cuTensorMapEncodeTiled failed for %s (%d)", w.name.c_str(), rc);
+      if (op.conv.xf.enabled && op.gn_gamma >= 0) {
+        op.conv.xf.gamma = h->raw_ptr(op.gn_gamma);
+        op.conv.xf.beta = h->raw_ptr(op.gn_gamma + 1);
+      }
     } else if (op.kind == Op::GN && op.gn_gamma >= 0) {
       op.gn.gamma = h->raw_ptr(op.gn_gamma);
       op.gn.beta = h->raw_ptr(op.gn_gamma + 1);
@@ -614,6 +629,10 @@ static int launch_op(r2dm_handle h, Op& op, const float* x, const float* film, c
     }
     case Op::CONV: {
       if (op.is_output) op.conv.out_nchw = pred;
+      if (op.xf_film) {
+        op.conv.xf.film = film; op.conv.xf.step_ptr = step_ptr;
+        op.conv.xf.rows_per_step = rows_per_step; op.conv.xf.row_batch_stride = row_batch_stride;
+      }
       CUDA_TRY(conv_launch(op.conv, s));
       break;
     }
@@ -792,6 +811,47 @@ int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const floa
     l.residual = res.ptr;
   }
   l.wpacked = wp; l.bias = bp; l.scale = scale;
+  int rc = conv_make_tmaps(l);
+  if (rc) return fail(-4, "tensor map encode failed (%d)", rc);
+  CUDA_TRY(conv_launch(l, s));
+  CUDA_TRY(unpack_nchw(dtype, l.out, y, 0, Cout, s));
+  return 0;
+}
+
+// GroupNorm/AdaGN(+SiLU) fused into the following convolution, exactly as the network runs it:
+// y = conv(silu(gn(x))) (+bias).  film: per-sample [B][2*Cin] = [scale || shift] or NULL (then gamma/beta).
+int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, const float* beta, const float* film,
+                    float eps, int silu, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                    int H, int W, void* scratch, size_t scratch_bytes, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (W % 128) return fail(-1, "W must be a multiple of 128");
+  if (Cin % (kNU * dtype_cw(dtype))) return fail(-1, "Cin must be a multiple of %d", kNU * dtype_cw(dtype));
+  Scratch sc{static_cast<uint8_t*>(scratch), scratch_bytes};
+  ConvLaunch l;
+  memset(&l, 0, sizeof(l));
+  l.dtype = dtype; l.taps = taps;
+  l.nt = pick_nt(taps, Cout);
+  l.cin_pad = round_up(Cin, conv_stage_channels(dtype, taps));
+  if (l.cin_pad != Cin) return fail(-1, "Cin must be a multiple of the stage K (%d)", conv_stage_channels(dtype, taps));
+  l.cout = Cout; l.cout_pad = round_up(Cout, l.nt);
+  if (taps == 9) l.ht = (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
+  else l.ht = H >= 2 ? 2 : 1;
+  PT probe; probe.B = B; probe.C = Cin; probe.H = H; probe.W = W;
+  l.in0 = make_pt(sc, dtype, B, Cin, H, W, tensor_stats_slots(dtype, probe));
+  l.out = make_pt(sc, dtype, B, l.cout_pad, H, W, 0);
+  void* wp = sc.take(conv_packed_weight_bytes(dtype, taps, l.nt, l.cin_pad, l.cout_pad));
+  float* bp = static_cast<float*>(sc.take(static_cast<size_t>(l.cout_pad) * 4));
+  if (!l.in0.ptr || !l.in0.stats || !l.out.ptr || !wp || !bp) return fail(-1, "scratch too small");
+  // NOTE: the input is stored unrounded here (it is a residual-stream tensor in the network)
+  CUDA_TRY(pack_nchw(dtype, x, B, Cin, H, W, l.in0, 0, s));
+  CUDA_TRY(tensor_stats_launch(dtype, l.in0, s));
+  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s));
+  CUDA_TRY(cudaMemsetAsync(bp, 0, static_cast<size_t>(l.cout_pad) * 4, s));
+  if (bias) CUDA_TRY(cudaMemcpyAsync(bp, bias, static_cast<size_t>(Cout) * 4, cudaMemcpyDeviceToDevice, s));
+  l.wpacked = wp; l.bias = bp; l.scale = 1.f;
+  l.xf.enabled = 1; l.xf.silu = silu; l.xf.groups = kNU; l.xf.eps = eps;
+  if (film) { l.xf.film = film; l.xf.film_stride = 2 * Cin; l.xf.film_off = 0; l.xf.row_batch_stride = 1; }
+  else { l.xf.gamma = gamma; l.xf.beta = beta; }
   int rc = conv_make_tmaps(l);
   if (rc) return fail(-4, "tensor map encode failed (%d)", rc);
   CUDA_TRY(conv_launch(l, s));

@@ -41,6 +41,25 @@ def conv2d(x, weight, bias=None, residual=None, scale=1.0, dtype="bf16"):
     return y
 
 
+def gn_conv2d(x, weight, bias=None, gamma=None, beta=None, film=None, eps=1e-6, silu=True, dtype="bf16"):
+    """conv(act(GroupNorm(x))) with the normalisation fused into the conv kernel's operand path, as the
+    network runs efficient_unet.py:99-106 (film [B, 2*Cin] = [scale || shift] selects AdaGN)."""
+    x = L.f32c(x)
+    w = L.f32c(weight)
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = w.shape
+    b = L.f32c(bias) if bias is not None else None
+    g = L.f32c(gamma) if gamma is not None else None
+    bt = L.f32c(beta) if beta is not None else None
+    f = L.f32c(film) if film is not None else None
+    y = torch.empty(B, Cout, H, W, device=x.device, dtype=torch.float32)
+    sc, n = _scratch(B, max(Cin, Cout), H, W, x.device)
+    L.check(L.lib().r2dm_op_gn_conv(_dt(dtype), kh * kw, L.ptr(x), L.ptr(g), L.ptr(bt), L.ptr(f), float(eps),
+                                    int(silu), L.ptr(w), L.ptr(b), L.ptr(y), B, Cin, Cout, H, W, L.ptr(sc), n,
+                                    L.stream_ptr()), "r2dm_op_gn_conv")
+    return y
+
+
 def group_norm(x, gamma=None, beta=None, film=None, eps=1e-6, silu=False, dtype="bf16"):
     """nn.GroupNorm(8, C, eps) (+SiLU); with `film` [B, 2C] = [scale || shift]: AdaGN (ops.py:196-199)."""
     x = L.f32c(x)

@@ -120,3 +120,35 @@ def test_attention_core(case, dtype):
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
     ref = (att @ v).transpose(1, 2).reshape(B, -1, E).transpose(1, 2).reshape(B, E, H, W)
     _check(y, ref, dtype, f"attention {case}", tf32_out=True)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("case", [(2, 64, 64, 8, 256, 3, False), (1, 128, 64, 4, 128, 3, True),
+                                  (2, 256, 128, 2, 128, 3, True), (1, 512, 1536, 4, 128, 1, False)])
+def test_fused_groupnorm_conv(case, dtype):
+    """The network's fused form: GroupNorm/AdaGN (+SiLU) applied to the operand tile inside the conv.
+    The normalised activations are rounded to the operand type (bf16 / tf32) before the MMA, so the
+    tolerance is that of an operand rounding: bf16 6e-3 l2-rel, tf32 1e-3."""
+    from r2dm_b200 import ops
+    B, Cin, Cout, H, W, k, film = case
+    g = torch.Generator().manual_seed(3)
+    x = _round_to(torch.randn(B, Cin, H, W, generator=g) * 1.3 + 0.2, dtype)
+    w = _round_to(torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k), dtype)
+    b = torch.randn(Cout, generator=g) * 0.1
+    silu = k == 3
+    if film:
+        ss = torch.randn(B, 2 * Cin, generator=g) * 0.3
+        h = O.group_norm(x, 8, 1e-6, None, None) * (1 + ss[:, :Cin, None, None]) + ss[:, Cin:, None, None]
+        kw = dict(film=ss.cuda())
+    else:
+        gm, bt = 1 + 0.1 * torch.randn(Cin, generator=g), 0.1 * torch.randn(Cin, generator=g)
+        h = O.group_norm(x, 8, 1e-6, gm, bt)
+        kw = dict(gamma=gm.cuda(), beta=bt.cuda())
+    if silu:
+        h = torch.nn.functional.silu(h)
+    ref = O.ring_conv3x3(h, w, b) if k == 3 else O.conv1x1(h, w, b)
+    y = ops.gn_conv2d(x.cuda(), w.cuda(), b.cuda(), eps=1e-6, silu=silu, dtype=dtype, **kw)
+    torch.cuda.synchronize()
+    e = rel_l2(y, ref)
+    tol = 6e-3 if dtype == "bf16" else 1e-3
+    assert e <= tol, f"fused gn+conv {case}[{dtype}]: l2-rel {e:.3e} > {tol}"
