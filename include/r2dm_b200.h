@@ -132,6 +132,9 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
 
 /* copy a named intermediate activation of the last forward to fp32 NCHW (debugging / tests);
  * returns channel count via *C_out etc.  Names: "in_conv", "<block>", "<block>.rb<i>". */
+/* developer aid: record a per-role globaltimer timeline of CTA 0 of subsequent conv launches into
+ * buf[4][cap] (uint64 ns; roles: producer, MMA, transform, epilogue); NULL disables. */
+int r2dm_debug_set_trace(void* buf, int cap);
 int r2dm_debug_tensor(r2dm_handle h, const char* name, float* out, int* C, int* H, int* W, void* stream);
 
 #ifdef __cplusplus

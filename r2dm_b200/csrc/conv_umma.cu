@@ -27,6 +27,7 @@
 //               NCHW store for the network output.
 // Elevation borders come from TMA out-of-bounds zero fill; the azimuth wrap from the halo columns.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "kernels.h"
@@ -46,6 +47,7 @@ struct XformParams {
   int film_stride, film_off;
   const int* step_ptr; int rows_per_step, row_batch_stride;
   int groups; float eps;
+  int debug;   // developer knob (R2DM_XF_DEBUG): 1 = skip transform math+copy, 2 = copy only
 };
 
 struct ConvParams {
@@ -61,10 +63,14 @@ struct ConvParams {
   int cout, cout_pad;     // real / padded output channels
   int nk, ksplit;         // pipeline stages over K; first stage that reads from tmap1
   int xtiles, ytiles, ntiles, tiles_total;
-  int unit_ch;            // output channels per statistics unit (cout / kNU)
+  int unit_ch;            // output channels per statistics unit (cout / kNU), a power of two
+  int unit_shift;         // log2(unit_ch)
   int slots;
   float scale;
   int stages, stage_bytes, wres;  // smem ring depth / stride; weights resident in smem
+  int debug;  // developer ablation knob (R2DM_CONV_DEBUG): 1 no epilogue stores, 2 no MMA issue, 4 no TMA
+  unsigned long long* trace;  // developer timeline (r2dm_debug_set_trace): [4 roles][cap] globaltimer ns of CTA 0
+  int trace_cap;
 };
 
 template <typename T, int NT, int HT, int TAPS, int KS>
@@ -87,10 +93,22 @@ struct ConvTraits {
   static_assert(B_BYTES % 128 == 0, "weight stage must stay 128B aligned");
 };
 
-__device__ __forceinline__ float silu_fast(float t) {  // 0.5 t (1 + tanh(t/2)), one MUFU op
+// silu(t) = h + h tanh(h) with h = t/2 (the 1/2 is folded into the affine coefficients): one MUFU op
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define R2DM_TRACE(role, idx)                                                          \
+  do {                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < p.trace_cap)                  \
+      p.trace[(role) * p.trace_cap + (idx)] = gtime();                                 \
+  } while (0)
+
+__device__ __forceinline__ float silu_from_half(float h) {
   float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * t));
-  return 0.5f * t * (1.f + th);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
 }
 
 template <typename T, int NT, int HT, int TAPS, int KS>
@@ -155,16 +173,19 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int ks = 0; ks < p.nk; ++ks, ++it) {
           const int st = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_wait_relaxed(&empty_bar[st], ph ^ 1, 2000);
           uint8_t* sa = smem_ring + static_cast<size_t>(st) * p.stage_bytes;
+          if (p.debug & 4) { mbar_arrive(&full_bar[st]); continue; }
           mbar_expect_tx(&full_bar[st], Tr::A_BYTES + (p.wres ? 0 : Tr::B_BYTES));
           const bool second = ks >= p.ksplit;
           const int plane0 = (second ? ks - p.ksplit : ks) * Tr::PLANES;
           const CUtensorMap* tm = second ? &p.tmap1 : &p.tmap0;
-          if (TAPS == 9) tma_load_5d(sa, tm, &full_bar[st], 0, x0, y0 - 1, plane0, b);
-          else tma_load_5d(sa, tm, &full_bar[st], 0, x0 + 1, y0, plane0, b);
+          // coordinates: (8-byte element within the padded row, half, row, plane, image)
+          if (TAPS == 9) tma_load_5d(sa, tm, &full_bar[st], 2 * x0, 0, y0 - 1, plane0, b);
+          else tma_load_5d(sa, tm, &full_bar[st], 2 * (x0 + 1), 0, y0, plane0, b);
           if (!p.wres)
             bulk_load(sa + Tr::A_BYTES_AL, wsrc + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES, &full_bar[st]);
+          R2DM_TRACE(0, it);
         }
       }
     }
@@ -175,7 +196,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       // descriptor halves: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 | version<<14 (no swizzle)
       const uint32_t a_lo_const = static_cast<uint32_t>(Tr::A_PLANE_BYTES >> 4) << 16;
       const uint32_t b_lo_const = static_cast<uint32_t>(Tr::B_PLANE_BYTES >> 4) << 16;
-      const uint32_t hi = (128u >> 4) | (1u << 14);
       if (p.wres) mbar_wait(&wres_bar, 0);
       uint32_t it = 0;
       int j = 0;
@@ -189,27 +209,36 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(p.xf.enabled ? &xf_bar[st] : &full_bar[st], ph);
           tc_fence_after();
+          R2DM_TRACE(1, 2 * it);
           const uint32_t sa = smem_u32(smem_ring + static_cast<size_t>(st) * p.stage_bytes);
           const uint32_t sb = p.wres ? smem_u32(smem_w) + static_cast<uint32_t>(ks) * Tr::B_BYTES : sa + Tr::A_BYTES_AL;
+          // low descriptor words of the stage bases; every operand below is base + compile-time
+          // constant (shared memory < 256 KB, so the 14-bit start-address field cannot carry)
+          const uint32_t a_lo0 = a_lo_const | ((sa >> 4) & 0x3FFFu);
+          const uint32_t b_lo0 = b_lo_const | ((sb >> 4) & 0x3FFFu);
+          // consecutive MMAs go to DIFFERENT accumulators (rows): back-to-back tcgen05.mma into the
+          // same TMEM tile serialise on the accumulate dependency (~110 cycles each, measured)
 #pragma unroll
-          for (int r = 0; r < HT; ++r) {
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
+            constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
 #pragma unroll
-            for (int tap = 0; tap < TAPS; ++tap) {
-              const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
-              const uint32_t a_off = static_cast<uint32_t>(((r + dy) * Tr::APITCH + dx) * 16);
+            for (int kk = 0; kk < KS; ++kk) {
 #pragma unroll
-              for (int kk = 0; kk < KS; ++kk) {
-                const uint32_t aa = sa + kk * 2 * Tr::A_PLANE_BYTES + a_off;
-                const uint32_t ba = sb + tap * Tr::B_TAP_BYTES + kk * 2 * Tr::B_PLANE_BYTES;
-                const uint64_t adesc = (static_cast<uint64_t>(hi) << 32) | (a_lo_const | ((aa >> 4) & 0x3FFFu));
-                const uint64_t bdesc = (static_cast<uint64_t>(hi) << 32) | (b_lo_const | ((ba >> 4) & 0x3FFFu));
+              for (int r = 0; r < HT; ++r) {
+                const uint32_t a_add = static_cast<uint32_t>((kk * 2 * Tr::A_PLANE_BYTES + ((r + dy) * Tr::APITCH + dx) * 16) >> 4);
+                const uint32_t b_add = static_cast<uint32_t>((tap * Tr::B_TAP_BYTES + kk * 2 * Tr::B_PLANE_BYTES) >> 4);
+                const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) | (a_lo0 + a_add);
+                const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) | (b_lo0 + b_add);
                 const uint32_t acc = (ks > 0 || tap > 0 || kk > 0) ? 1u : 0u;
+                if (p.debug & 2) continue;
                 if (Elem<T>::kFmt == 2) umma_tf32(dbase + r * NT, adesc, bdesc, idesc, acc);
                 else umma_f16(dbase + r * NT, adesc, bdesc, idesc, acc);
               }
             }
           }
           umma_commit(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
+          R2DM_TRACE(1, 2 * it + 1);
         }
         umma_commit(&acc_full[buf]);
       }
@@ -271,13 +300,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             const int row = (p.xf.step_ptr ? *p.xf.step_ptr : 0) * p.xf.rows_per_step + b * p.xf.row_batch_stride;
             fl = p.xf.film + static_cast<size_t>(row) * p.xf.film_stride + p.xf.film_off;
           }
+          // with the fast SiLU the coefficients produce h = t/2 directly
+          const float fold = (p.xf.silu && sizeof(T) == 2) ? 0.5f : 1.f;
           for (int c = tt; c < Ctot; c += 128) {
             const int g = c / gsize;
             const float ga = fl ? 1.f + fl[c] : p.xf.gamma[c];
             const float be = fl ? fl[Ctot + c] : p.xf.beta[c];
             const float a = grp_s[1][g] * ga;
-            coef_s[0][c] = a;
-            coef_s[1][c] = be - grp_s[0][g] * a;
+            coef_s[0][c] = a * fold;
+            coef_s[1][c] = (be - grp_s[0][g] * a) * fold;
           }
           asm volatile("bar.sync 2, 128;" ::: "memory");
         }
@@ -295,10 +326,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             ca[i] = ok ? coef_s[0][c0 + i] : 0.f;
             cd[i] = ok ? coef_s[1][c0 + i] : 0.f;
           }
-          mbar_wait(&full_bar[st], ph);
+          mbar_wait_relaxed(&full_bar[st], ph, 500);
+          if (tt == 0) R2DM_TRACE(2, 2 * it);
           uint4* base = reinterpret_cast<uint4*>(smem_ring + static_cast<size_t>(st) * p.stage_bytes +
                                                  my_plane * Tr::A_PLANE_BYTES) + row_lo * Tr::APITCH;
-          if (c0 < Ctot) {
+          if (c0 < Ctot && p.xf.debug == 2) {
+#pragma unroll 4
+            for (int i = tip; i < n_units; i += TPP) base[i] = base[i];
+          } else if (c0 < Ctot && p.xf.debug == 0) {
 #pragma unroll 4
             for (int i = tip; i < n_units; i += TPP) {
               float v[CW];
@@ -306,7 +341,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
               for (int k = 0; k < CW; ++k) {
                 const float tv = fmaf(v[k], ca[k], cd[k]);
-                v[k] = p.xf.silu ? (sizeof(T) == 2 ? silu_fast(tv) : silu_f(tv)) : tv;
+                v[k] = p.xf.silu ? (sizeof(T) == 2 ? silu_from_half(tv) : silu_f(tv)) : tv;
               }
               base[i] = Elem<T>::pack_mma(v);
             }
@@ -314,6 +349,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&xf_bar[st]);
+          if (tt == 0) R2DM_TRACE(2, 2 * it + 1);
         }
       }
     }
@@ -336,22 +372,27 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       decode(t, b, yt, xt, nt);
       const int n0 = nt * NT, x = xt * 128 + m, y0 = yt * HT;
       const int buf = j & 1;
-      float sacc[NUT][2];
+      // GroupNorm partial sums per 8-channel chunk of the columns this warp visits (compile-time
+      // indexed registers); chunks are folded into statistics units once per tile
+      constexpr int CCOLS = HT > 1 ? NT : NT / 2;       // columns visited by this warp
+      constexpr int NCH = CCOLS / 8 > 0 ? CCOLS / 8 : 1;
+      float sacc[NCH][2];
 #pragma unroll
-      for (int u = 0; u < NUT; ++u) { sacc[u][0] = 0.f; sacc[u][1] = 0.f; }
-      mbar_wait(&acc_full[buf], (j >> 1) & 1);
+      for (int u = 0; u < NCH; ++u) { sacc[u][0] = 0.f; sacc[u][1] = 0.f; }
+      mbar_wait_relaxed(&acc_full[buf], (j >> 1) & 1, 1000);
       tc_fence_after();
+      if (ethread == 0) R2DM_TRACE(3, 3 * j);
       const uint32_t tbase = tmem + buf * Tr::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
       constexpr int RSTEP = HT > 1 ? 2 : 1;
       const int r_begin = HT > 1 ? half : 0;
       const int c_begin = HT > 1 ? 0 : half * (NT / 2);
-      const int c_end = HT > 1 ? NT : c_begin + NT / 2;
 #pragma unroll 1
       for (int r = r_begin; r < HT; r += RSTEP) {
         const int y = y0 + r;
         if (y >= p.H) break;
-#pragma unroll 1
-        for (int c0 = c_begin; c0 < c_end; c0 += CB) {
+#pragma unroll
+        for (int cb = 0; cb < CCOLS; cb += CB) {
+          const int c0 = c_begin + cb;
           // residual prefetch (independent loads in flight while TMEM is read)
           uint4 rr[CB / CW];
           if (res != nullptr && p.out_nchw == nullptr) {
@@ -393,13 +434,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             }
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-            for (int i = 0; i < CW; ++i) { o[i] *= p.scale; s1 += o[i]; s2 += o[i] * o[i]; }
-            if (p.stats != nullptr) {
-              const int un = cl / p.unit_ch;
-#pragma unroll
-              for (int qq = 0; qq < NUT; ++qq)
-                if (qq == un) { sacc[qq][0] += s1; sacc[qq][1] += s2; }
-            }
+            for (int i = 0; i < CW; ++i) { o[i] *= p.scale; s1 += o[i]; s2 = fmaf(o[i], o[i], s2); }
+            sacc[(cb + u * CW) / 8][0] += s1;
+            sacc[(cb + u * CW) / 8][1] += s2;
             const uint4 pk = Elem<T>::pack(o);
             out[idx] = pk;
             if (x == 0) out[idx + p.W] = pk;              // xp = W+1 mirrors pixel 0
@@ -411,20 +448,35 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (ethread == 0) R2DM_TRACE(3, 3 * j + 1);
       if (p.stats != nullptr) {
+        // fold chunk sums into statistics units (unit_ch = 8 << k channels), then across lanes/warps
         const int par = j & 1;
+        const int cpu = p.unit_ch >> 3;                  // chunks per unit (power of two)
+        const int units_w = NCH / cpu;                   // units visited by this warp
+        const int unit0_w = (c_begin >> 3) / cpu;        // first unit of this warp within the tile
 #pragma unroll
         for (int u = 0; u < NUT; ++u) {
-          const float a = warp_sum(sacc[u][0]), qv = warp_sum(sacc[u][1]);
-          if (lane == 0) { stat_s[par][ew][u][0] = a; stat_s[par][ew][u][1] = qv; }
+          if (u < units_w) {
+            float a = 0.f, qv = 0.f;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+              if ((c >> (p.unit_shift - 3)) == u) { a += sacc[c][0]; qv += sacc[c][1]; }
+            a = warp_sum(a); qv = warp_sum(qv);
+            if (lane == 0) { stat_s[par][ew][unit0_w + u][0] = a; stat_s[par][ew][unit0_w + u][1] = qv; }
+          }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int units_here = NT / p.unit_ch;
         if (ethread < units_here * 2) {
           const int u = ethread >> 1, k = ethread & 1;
           float tot = 0.f;
+          // HT > 1: every warp saw all units; HT == 1: warps 0-3 saw the lower half, 4-7 the upper
 #pragma unroll
-          for (int w = 0; w < 8; ++w) tot += stat_s[par][w][u][k];
+          for (int w = 0; w < 8; ++w) {
+            const bool has = HT > 1 ? true : ((w >> 2) == (u >= units_here / 2 ? 1 : 0)) || units_here == 1;
+            if (has) tot += stat_s[par][w][u][k];
+          }
           const int unit = n0 / p.unit_ch + u;
           const int slot = yt * p.xtiles + xt;
           p.stats[((static_cast<size_t>(b) * kNU + unit) * p.slots + slot) * 2 + k] = tot;
@@ -463,18 +515,25 @@ size_t conv_packed_weight_bytes(int dtype, int taps, int nt, int cin_pad, int co
 
 int conv_stat_slots(const ConvLaunch& l) { return (l.out.H / l.ht) * (l.out.W / 128); }
 
+// The planar-16 tensor [B][planes][H][Wp][16 B] is described to the TMA unit with 8-byte elements
+// and the pixel axis split in two halves (dim1, stride = half a box row) so that one inner box
+// segment is box_w*8 bytes (1040 B) instead of 16 B: a 16-byte inner dimension makes the TMA
+// unit issue one request per pixel-plane and was the bottleneck of the first version.
+//   dims (fastest first): [2*Wp elements of 8 B][2 halves][H][planes][B]
+//   box                 : [box_w elements][2][box_h][box_planes][1]   -> box_w pixels x 16 B per row
 static int make_one_tmap(CUtensorMap* tm, int dtype, const PT& t, int box_w, int box_h, int box_planes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
   const int cw = dtype_cw(dtype);
   const cuuint64_t Wp = t.W + 2;
-  cuuint64_t dims[5] = {(cuuint64_t)cw, Wp, (cuuint64_t)t.H, (cuuint64_t)(t.C / cw), (cuuint64_t)t.B};
-  cuuint64_t strides[4] = {16, Wp * 16, (cuuint64_t)t.H * Wp * 16, (cuuint64_t)(t.C / cw) * t.H * Wp * 16};
-  cuuint32_t box[5] = {(cuuint32_t)cw, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_planes, 1};
+  cuuint64_t dims[5] = {2 * Wp, 2, (cuuint64_t)t.H, (cuuint64_t)(t.C / cw), (cuuint64_t)t.B};
+  cuuint64_t strides[4] = {(cuuint64_t)box_w * 8, Wp * 16, (cuuint64_t)t.H * Wp * 16,
+                           (cuuint64_t)(t.C / cw) * t.H * Wp * 16};
+  cuuint32_t box[5] = {(cuuint32_t)box_w, 2, (cuuint32_t)box_h, (cuuint32_t)box_planes, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(tm, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
-                   t.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, t.ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
@@ -497,6 +556,10 @@ static int num_sms() {
   }
   return n;
 }
+
+static unsigned long long* g_trace = nullptr;
+static int g_trace_cap = 0;
+void conv_set_trace(unsigned long long* buf, int cap) { g_trace = buf; g_trace_cap = cap; }
 
 constexpr int kSmemBudget = 216 * 1024;     // dynamic smem per CTA (227 KB limit minus ~9.5 KB static)
 constexpr int kWresMaxBytes = 80 * 1024;    // keep the filter bank resident below this size
@@ -522,7 +585,10 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.ksplit = l.in1.ptr ? l.in0.C / Tr::KCH : p.nk;
   p.xtiles = l.out.W / 128; p.ytiles = (l.out.H + HT - 1) / HT; p.ntiles = l.cout_pad / NT;
   p.tiles_total = p.B * p.ytiles * p.xtiles * p.ntiles;
-  p.unit_ch = l.cout / kNU > 0 ? l.cout / kNU : 1;
+  p.unit_ch = l.cout / kNU >= 8 ? l.cout / kNU : 8;
+  p.unit_shift = 0;
+  while ((1 << p.unit_shift) < p.unit_ch) ++p.unit_shift;
+  if (p.stats != nullptr && ((1 << p.unit_shift) != p.unit_ch || p.unit_ch > NT)) return cudaErrorInvalidValue;
   p.slots = l.out.slots;
   p.scale = l.scale;
   // operand transform (fused GroupNorm / AdaGN + SiLU)
@@ -535,6 +601,9 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
     x.film_stride = l.xf.film_stride; x.film_off = l.xf.film_off;
     x.step_ptr = l.xf.step_ptr; x.rows_per_step = l.xf.rows_per_step; x.row_batch_stride = l.xf.row_batch_stride;
     x.groups = l.xf.groups; x.eps = l.xf.eps;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("R2DM_XF_DEBUG"); dbg = e ? atoi(e) : 0; }
+    x.debug = dbg;
     if (x.C0 + x.C1 > kMaxCin || x.stats0 == nullptr) return cudaErrorInvalidValue;
   }
   // shared-memory plan: resident weights when the whole bank of this N tile fits, then as many
@@ -548,6 +617,12 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   if (stages < 2) return cudaErrorInvalidConfiguration;
   p.stages = stages;
   const int smem = 256 + (p.wres ? static_cast<int>(wbytes) : 0) + stages * p.stage_bytes;
+  p.trace = g_trace; p.trace_cap = g_trace_cap;
+  {
+    static int cdbg = -1;
+    if (cdbg < 0) { const char* e = getenv("R2DM_CONV_DEBUG"); cdbg = e ? atoi(e) : 0; }
+    p.debug = cdbg;
+  }
   int grid = num_sms();
   if (grid > p.tiles_total) grid = p.tiles_total;
   kern<<<grid, 512, smem, s>>>(p);

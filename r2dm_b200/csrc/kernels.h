@@ -58,6 +58,8 @@ int conv_stage_channels(int dtype, int taps);  // K per pipeline stage
 size_t conv_packed_weight_bytes(int dtype, int taps, int nt, int cin_pad, int cout_pad);
 int conv_stat_slots(const ConvLaunch& l);
 cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s);
+// developer timeline of CTA 0 of subsequent conv launches: buf[4 roles][cap] (globaltimer ns), or null
+void conv_set_trace(unsigned long long* buf, int cap);
 // w: fp32 [cout][cin][k][k] (OIHW), k*k == taps
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin,
                              int cin_pad, int cout_pad, void* dst, cudaStream_t s);

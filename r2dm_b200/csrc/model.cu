@@ -913,6 +913,11 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
   return 0;
 }
 
+int r2dm_debug_set_trace(void* buf, int cap) {
+  conv_set_trace(static_cast<unsigned long long*>(buf), cap);
+  return 0;
+}
+
 int r2dm_debug_tensor(r2dm_handle h, const char* name, float* out, int* C, int* H, int* W, void* stream) {
   if (!h || !name) return fail(-1, "null argument");
   auto it = h->named.find(name);
