@@ -537,6 +537,12 @@ static int make_one_tmap(CUtensorMap* tm, int dtype, const PT& t, int box_w, int
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
+// qkv tensor map for the attention kernel: box = 128 pixels of one row x (hd/8) planes
+int attention_make_tmap(CUtensorMap* tm, const PT& qkv, int heads) {
+  const int hd = qkv.C / 3 / heads;
+  return make_one_tmap(tm, kBF16, qkv, 128, 1, hd / 8);
+}
+
 int conv_make_tmaps(ConvLaunch& l) {
   const int planes = 2 * ks_for(l.taps);
   const int bw = l.taps == 9 ? 130 : 128, bh = l.taps == 9 ? l.ht + 2 : l.ht;

@@ -99,7 +99,10 @@ cudaError_t up2_launch(int dtype, PT src, PT dst, cudaStream_t s);
 
 // ------------------------------------------------------------------ attention core
 // qkv: planar-16 tensor with 3E channels ([q;k;v]); out: E channels. softmax(q k^T / sqrt(hd)) v
-cudaError_t attention_launch(int dtype, PT qkv, PT out, int heads, cudaStream_t s);
+cudaError_t attention_launch(int dtype, PT qkv, PT out, int heads, cudaStream_t s);   // exact fp32 FMA-pipe version
+// bf16 tensor-core version (tcgen05): needs a TMA map of the qkv tensor
+int attention_make_tmap(CUtensorMap* tm, const PT& qkv, int heads);
+cudaError_t attention_umma_launch(PT qkv, PT out, int heads, const CUtensorMap& tm, cudaStream_t s);
 
 // ------------------------------------------------------------------ conditioning table
 struct CondEmbed {

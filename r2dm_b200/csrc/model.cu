@@ -62,6 +62,7 @@ struct Op {
   int gn_gamma = -1;      // raw index of gamma (beta = +1), or -1 for AdaGN
   bool is_output = false; // network output conv (writes pred NCHW)
   bool xf_film = false;   // conv with fused AdaGN: film pointers patched per forward
+  CUtensorMap attn_tmap;  // ATTN (bf16): TMA map of the packed qkv tensor
 };
 
 }  // namespace
@@ -582,6 +583,9 @@ int r2dm_bind_workspace(r2dm_handle h, void* workspace, size_t bytes, int batch,
         op.conv.xf.gamma = h->raw_ptr(op.gn_gamma);
         op.conv.xf.beta = h->raw_ptr(op.gn_gamma + 1);
       }
+    } else if (op.kind == Op::ATTN && h->dtype == kBF16) {
+      int rc = attention_make_tmap(&op.attn_tmap, op.a, op.heads);
+      if (rc) return fail(-4, "cuTensorMapEncodeTiled failed for attention (%d)", rc);
     } else if (op.kind == Op::GN && op.gn_gamma >= 0) {
       op.gn.gamma = h->raw_ptr(op.gn_gamma);
       op.gn.beta = h->raw_ptr(op.gn_gamma + 1);
@@ -646,7 +650,10 @@ static int launch_op(r2dm_handle h, Op& op, const float* x, const float* film, c
     }
     case Op::DOWN: CUDA_TRY(down2_launch(h->dtype, op.a, op.b, s)); break;
     case Op::UP: CUDA_TRY(up2_launch(h->dtype, op.a, op.b, s)); break;
-    case Op::ATTN: CUDA_TRY(attention_launch(h->dtype, op.a, op.b, op.heads, s)); break;
+    case Op::ATTN:
+      if (h->dtype == kBF16) CUDA_TRY(attention_umma_launch(op.a, op.b, op.heads, op.attn_tmap, s));
+      else CUDA_TRY(attention_launch(h->dtype, op.a, op.b, op.heads, s));
+      break;
   }
   return 0;
 }
@@ -908,7 +915,14 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
   PT out = make_pt(sc, dtype, B, E, H, W, 0);
   if (!in.ptr || !out.ptr) return fail(-1, "scratch too small");
   CUDA_TRY(pack_nchw(dtype, qkv, B, 3 * E, H, W, in, 0, s));
-  CUDA_TRY(attention_launch(dtype, in, out, heads, s));
+  if (dtype == kBF16) {
+    CUtensorMap tm;
+    int rc = attention_make_tmap(&tm, in, heads);
+    if (rc) return fail(-4, "tensor map encode failed (%d)", rc);
+    CUDA_TRY(attention_umma_launch(in, out, heads, tm, s));
+  } else {
+    CUDA_TRY(attention_launch(dtype, in, out, heads, s));
+  }
   CUDA_TRY(unpack_nchw(dtype, out, y, 0, E, s));
   return 0;
 }
