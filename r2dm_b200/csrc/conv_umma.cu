@@ -328,22 +328,31 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           }
           mbar_wait_relaxed(&full_bar[st], ph, 500);
           if (tt == 0) R2DM_TRACE(2, 2 * it);
-          uint4* base = reinterpret_cast<uint4*>(smem_ring + static_cast<size_t>(st) * p.stage_bytes +
-                                                 my_plane * Tr::A_PLANE_BYTES) + row_lo * Tr::APITCH;
-          if (c0 < Ctot && p.xf.debug == 2) {
-#pragma unroll 4
-            for (int i = tip; i < n_units; i += TPP) base[i] = base[i];
-          } else if (c0 < Ctot && p.xf.debug == 0) {
-#pragma unroll 4
-            for (int i = tip; i < n_units; i += TPP) {
-              float v[CW];
-              Elem<T>::unpack(base[i], v);
+          const uint32_t sbase = smem_u32(smem_ring + static_cast<size_t>(st) * p.stage_bytes +
+                                          my_plane * Tr::A_PLANE_BYTES) + row_lo * Tr::APITCH * 16;
+          if (c0 < Ctot && (p.xf.debug == 0 || p.xf.debug == 3)) {
+            // batches of XB units: all loads first, then the math, then the stores (the plain
+            // pointer version compiled into a serial load -> math -> store chain per unit)
+            constexpr int XB = 4;
+            for (int i0 = tip; i0 < n_units; i0 += XB * TPP) {
+              uint4 raw[XB];
 #pragma unroll
-              for (int k = 0; k < CW; ++k) {
-                const float tv = fmaf(v[k], ca[k], cd[k]);
-                v[k] = p.xf.silu ? (sizeof(T) == 2 ? silu_from_half(tv) : silu_f(tv)) : tv;
+              for (int u = 0; u < XB; ++u)
+                if (i0 + u * TPP < n_units) raw[u] = lds128(sbase + (i0 + u * TPP) * 16);
+#pragma unroll
+              for (int u = 0; u < XB; ++u) {
+                float v[CW];
+                Elem<T>::unpack(raw[u], v);
+#pragma unroll
+                for (int k = 0; k < CW; ++k) {
+                  const float tv = fmaf(v[k], ca[k], cd[k]);
+                  v[k] = (p.xf.silu && p.xf.debug != 3) ? (sizeof(T) == 2 ? silu_from_half(tv) : silu_f(tv)) : tv;
+                }
+                raw[u] = Elem<T>::pack_mma(v);
               }
-              base[i] = Elem<T>::pack_mma(v);
+#pragma unroll
+              for (int u = 0; u < XB; ++u)
+                if (i0 + u * TPP < n_units) sts128(sbase + (i0 + u * TPP) * 16, raw[u]);
             }
           }
           fence_proxy_async_smem();
