@@ -83,9 +83,15 @@ struct ConvTraits {
   static constexpr int A_PLANE_BYTES = AROWS * APITCH * 16;
   static constexpr int A_BYTES = PLANES * A_PLANE_BYTES;
   static constexpr int A_BYTES_AL = (A_BYTES + 127) / 128 * 128;
-  static constexpr int B_PLANE_BYTES = NT * 16;
-  static constexpr int B_TAP_BYTES = PLANES * B_PLANE_BYTES;
-  static constexpr int B_BYTES = TAPS * B_TAP_BYTES;
+  // FUSE (3x3, NT = 64): the three vertical taps of one horizontal offset are ONE MMA with N = 192:
+  // the shifted A view of input row i feeds output rows i-1, i, i+1 (adjacent accumulator column
+  // blocks), because a 128x64x16 MMA cannot go below ~60 cycles (53 % of the tensor pipe, measured
+  // with tools/probe_mma_rate.cu) while N >= 128 runs at full rate.  Weights are then packed as
+  // [kx][plane][ky descending][co] so that any contiguous ky range is a contiguous row range of B.
+  static constexpr bool FUSE = (TAPS == 9 && NT == 64);
+  static constexpr int B_PLANE_BYTES = (FUSE ? 3 : 1) * NT * 16;
+  static constexpr int B_TAP_BYTES = PLANES * B_PLANE_BYTES;          // one tap (or one kx block)
+  static constexpr int B_BYTES = (FUSE ? 3 : TAPS) * B_TAP_BYTES;
   static constexpr int ACC_COLS = HT * NT;
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
                                    : 2 * ACC_COLS <= 256 ? 256 : 512;
@@ -193,6 +199,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, NT, Elem<T>::kFmt);
+      const uint32_t idesc2 = make_idesc(128, 2 * NT <= 256 ? 2 * NT : NT, Elem<T>::kFmt);
+      const uint32_t idesc3 = make_idesc(128, 3 * NT <= 256 ? 3 * NT : NT, Elem<T>::kFmt);
+      (void)idesc2; (void)idesc3;
       // descriptor halves: lo = start>>4 | LBO>>4 << 16 ; hi = SBO>>4 | version<<14 (no swizzle)
       const uint32_t a_lo_const = static_cast<uint32_t>(Tr::A_PLANE_BYTES >> 4) << 16;
       const uint32_t b_lo_const = static_cast<uint32_t>(Tr::B_PLANE_BYTES >> 4) << 16;
@@ -216,24 +225,64 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           // constant (shared memory < 256 KB, so the 14-bit start-address field cannot carry)
           const uint32_t a_lo0 = a_lo_const | ((sa >> 4) & 0x3FFFu);
           const uint32_t b_lo0 = b_lo_const | ((sb >> 4) & 0x3FFFu);
-          // consecutive MMAs go to DIFFERENT accumulators (rows): back-to-back tcgen05.mma into the
-          // same TMEM tile serialise on the accumulate dependency (~110 cycles each, measured)
+          constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
+          if constexpr (Tr::FUSE) {
 #pragma unroll
-          for (int tap = 0; tap < TAPS; ++tap) {
-            const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
-            constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
+            for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-            for (int kk = 0; kk < KS; ++kk) {
+              for (int kk = 0; kk < KS; ++kk) {
+                const uint32_t a_k = static_cast<uint32_t>((kk * 2 * Tr::A_PLANE_BYTES + kx * 16) >> 4);
+                const uint32_t b_k = static_cast<uint32_t>((kx * Tr::B_TAP_BYTES + kk * 2 * Tr::B_PLANE_BYTES) >> 4);
+                if (ks == 0 && kx == 0 && kk == 0) {
+                  // first touch of the accumulators: per-tap N = 64 MMAs so that the accumulate
+                  // flag can be cleared per output row
 #pragma unroll
-              for (int r = 0; r < HT; ++r) {
-                const uint32_t a_add = static_cast<uint32_t>((kk * 2 * Tr::A_PLANE_BYTES + ((r + dy) * Tr::APITCH + dx) * 16) >> 4);
-                const uint32_t b_add = static_cast<uint32_t>((tap * Tr::B_TAP_BYTES + kk * 2 * Tr::B_PLANE_BYTES) >> 4);
-                const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) | (a_lo0 + a_add);
-                const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) | (b_lo0 + b_add);
-                const uint32_t acc = (ks > 0 || tap > 0 || kk > 0) ? 1u : 0u;
-                if (p.debug & 2) continue;
-                if (Elem<T>::kFmt == 2) umma_tf32(dbase + r * NT, adesc, bdesc, idesc, acc);
-                else umma_f16(dbase + r * NT, adesc, bdesc, idesc, acc);
+                  for (int r = 0; r < HT; ++r) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                      const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) |
+                                             (a_lo0 + a_k + static_cast<uint32_t>(((r + ky) * Tr::APITCH * 16) >> 4));
+                      const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
+                                             (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky) * NT * 16) >> 4));
+                      if (p.debug & 2) continue;
+                      if (Elem<T>::kFmt == 2) umma_tf32(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
+                      else umma_f16(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int ir = 0; ir < HT + 2; ++ir) {
+                    const int r_lo = ir - 2 > 0 ? ir - 2 : 0, r_hi = ir < HT - 1 ? ir : HT - 1;
+                    const int ky_hi = ir - r_lo, nrows = r_hi - r_lo + 1;
+                    const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) |
+                                           (a_lo0 + a_k + static_cast<uint32_t>((ir * Tr::APITCH * 16) >> 4));
+                    const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
+                                           (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky_hi) * NT * 16) >> 4));
+                    const uint32_t idn = nrows == 3 ? idesc3 : (nrows == 2 ? idesc2 : idesc);
+                    if (p.debug & 2) continue;
+                    if (Elem<T>::kFmt == 2) umma_tf32(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
+                    else umma_f16(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
+                  }
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const int dy = TAPS == 9 ? tap / 3 : 0, dx = TAPS == 9 ? tap % 3 : 0;
+#pragma unroll
+              for (int kk = 0; kk < KS; ++kk) {
+#pragma unroll
+                for (int r = 0; r < HT; ++r) {
+                  const uint32_t a_add = static_cast<uint32_t>((kk * 2 * Tr::A_PLANE_BYTES + ((r + dy) * Tr::APITCH + dx) * 16) >> 4);
+                  const uint32_t b_add = static_cast<uint32_t>((tap * Tr::B_TAP_BYTES + kk * 2 * Tr::B_PLANE_BYTES) >> 4);
+                  const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) | (a_lo0 + a_add);
+                  const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) | (b_lo0 + b_add);
+                  const uint32_t acc = (ks > 0 || tap > 0 || kk > 0) ? 1u : 0u;
+                  if (p.debug & 2) continue;
+                  if (Elem<T>::kFmt == 2) umma_tf32(dbase + r * NT, adesc, bdesc, idesc, acc);
+                  else umma_f16(dbase + r * NT, adesc, bdesc, idesc, acc);
+                }
               }
             }
           }
@@ -668,10 +717,11 @@ cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------ weights
-// dst[nt][ks][tap][plane][co][cw]  <-  w[co][ci][tap]   (zero padded)
+// dst[nt][ks][tap][plane][co][cw]  <-  w[co][ci][tap]   (zero padded); with fuse_dy (3x3, nt = 64)
+// the order inside a stage is [kx][plane][ky descending][co][cw] (see ConvTraits::FUSE)
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int taps, int nt,
-                                   int cout, int cin, int cin_pad, int cout_pad, int planes) {
+                                   int cout, int cin, int cin_pad, int cout_pad, int planes, int fuse_dy) {
   constexpr int CW = Elem<T>::CW;
   const size_t total = static_cast<size_t>(taps) * cin_pad * cout_pad;
   const int kch = planes * CW;
@@ -681,8 +731,16 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     size_t r = i;
     const int cw = r % CW; r /= CW;
     const int co = r % nt; r /= nt;
-    const int pl = r % planes; r /= planes;
-    const int tap = r % taps; r /= taps;
+    int pl, tap;
+    if (fuse_dy) {
+      const int kyd = r % 3; r /= 3;
+      pl = r % planes; r /= planes;
+      const int kx = r % 3; r /= 3;
+      tap = (2 - kyd) * 3 + kx;
+    } else {
+      pl = r % planes; r /= planes;
+      tap = r % taps; r /= taps;
+    }
     const int ks = r % nk; r /= nk;
     const int nti = static_cast<int>(r);
     const int ci = ks * kch + pl * CW + cw;
@@ -690,9 +748,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     float v = 0.f;
     if (ci < cin && o < cout) v = w[(static_cast<size_t>(o) * cin + ci) * taps + tap];
     if (sizeof(T) == 4) {  // tf32 operand: round to nearest instead of the tensor core's truncation
-      uint32_t r;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-      v = __uint_as_float(r);
+      uint32_t rr;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v));
+      v = __uint_as_float(rr);
     }
     dst[i] = static_cast<T>(v);
   }
@@ -701,14 +759,15 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin, int cin_pad,
                              int cout_pad, void* dst, cudaStream_t s) {
   const int planes = 2 * ks_for(taps);
+  const int fuse = (taps == 9 && nt == 64) ? 1 : 0;
   const size_t total = static_cast<size_t>(taps) * cin_pad * cout_pad;
   const int grid = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   if (dtype == kBF16)
     pack_weight_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(w, static_cast<__nv_bfloat16*>(dst), taps, nt, cout,
-                                                           cin, cin_pad, cout_pad, planes);
+                                                           cin, cin_pad, cout_pad, planes, fuse);
   else
     pack_weight_kernel<float><<<grid, 256, 0, s>>>(w, static_cast<float*>(dst), taps, nt, cout, cin, cin_pad,
-                                                   cout_pad, planes);
+                                                   cout_pad, planes, fuse);
   return cudaGetLastError();
 }
 
