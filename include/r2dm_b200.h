@@ -99,6 +99,10 @@ int r2dm_sampler_update(float* x_out, const float* x, const float* pred, const f
 /* y[b] = ac[b][0]*x[b] + ac[b][1]*noise[b]  (q_step / q_step_from_x_0, continuous_time.py:169-190) */
 int r2dm_axpby(float* y, const float* x, const float* noise, const float* ac, int batch,
                size_t per_sample, void* stream);
+/* same with a per-step table: row = (step_ptr ? *step_ptr : 0)*rows_per_step + b*row_batch_stride,
+ * y[b] = table[row][0]*x[b] + table[row][1]*noise[b]  (RePaint re-noising under a CUDA graph) */
+int r2dm_axpby_table(float* y, const float* x, const float* noise, const float* table, const int* step_ptr,
+                     int rows_per_step, int row_batch_stride, int batch, size_t per_sample, void* stream);
 int r2dm_advance_step(int* step_ptr, int delta, void* stream);
 
 /* --- LiDAR post-processing (sample_and_save.py:52-57, utils/lidar.py:49-70,99-120):

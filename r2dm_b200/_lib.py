@@ -62,6 +62,7 @@ _SIGS = {
     "r2dm_sampler_update": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_float,
                                       _P, _P, _P, C.c_int, C.c_size_t, _P]),
     "r2dm_axpby": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_size_t, _P]),
+    "r2dm_axpby_table": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_size_t, _P]),
     "r2dm_advance_step": (C.c_int, [_P, C.c_int, _P]),
     "r2dm_lidar_postprocess": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_float, _P]),

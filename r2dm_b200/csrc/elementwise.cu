@@ -542,9 +542,11 @@ cudaError_t sampler_update_launch(const SamplerUpdate& u, cudaStream_t s) {
 
 __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, const float* __restrict__ noise,
                                                     const float* __restrict__ ac, float* __restrict__ y,
-                                                    size_t per_sample) {
+                                                    size_t per_sample, const int* __restrict__ step_ptr,
+                                                    int rows_per_step, int row_batch_stride) {
   const int b = blockIdx.y;
-  const float a = ac[2 * b], c = ac[2 * b + 1];
+  const int row = (step_ptr ? *step_ptr : 0) * rows_per_step + b * row_batch_stride;
+  const float a = ac[2 * row], c = ac[2 * row + 1];
   const size_t n4 = per_sample / 4;
   const float4* xv = reinterpret_cast<const float4*>(x + b * per_sample);
   const float4* nv = reinterpret_cast<const float4*>(noise + b * per_sample);
@@ -557,11 +559,11 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x,
 }
 
 cudaError_t axpby_launch(const float* x, const float* noise, const float* ac, float* y, int B, size_t per_sample,
-                         cudaStream_t s) {
+                         const int* step_ptr, int rows_per_step, int row_batch_stride, cudaStream_t s) {
   if (per_sample % 4 != 0) return cudaErrorInvalidValue;
   int gx = static_cast<int>((per_sample / 4 + 255) / 256);
   if (gx > 148 * 4) gx = 148 * 4;
-  axpby_kernel<<<dim3(gx, B), 256, 0, s>>>(x, noise, ac, y, per_sample);
+  axpby_kernel<<<dim3(gx, B), 256, 0, s>>>(x, noise, ac, y, per_sample, step_ptr, rows_per_step, row_batch_stride);
   return cudaGetLastError();
 }
 

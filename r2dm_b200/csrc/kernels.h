@@ -131,9 +131,11 @@ struct SamplerUpdate {
   int B; size_t per_sample;
 };
 cudaError_t sampler_update_launch(const SamplerUpdate& u, cudaStream_t s);
-// y = a[b]*x + c[b]*noise  (q_step / q_step_from_x_0), coefficients on device: ac[b][2]
+// y = a*x + c*noise  (q_step / q_step_from_x_0), coefficients on device: ac[row][2],
+// row = step*rows_per_step + b*row_batch_stride (step_ptr may be null -> 0)
 cudaError_t axpby_launch(const float* x, const float* noise, const float* ac, float* y, int B,
-                         size_t per_sample, cudaStream_t s);
+                         size_t per_sample, const int* step_ptr, int rows_per_step, int row_batch_stride,
+                         cudaStream_t s);
 cudaError_t advance_step_launch(int* step_ptr, int delta, cudaStream_t s);
 // [depth, x, y, z, reflectance] from a sample in [-1, 1] (sample_and_save.py:52-57)
 cudaError_t lidar_postprocess_launch(const float* sample, const float* angles, float* out, int B,

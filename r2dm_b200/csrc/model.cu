@@ -742,7 +742,15 @@ int r2dm_sampler_update(float* x_out, const float* x, const float* pred, const f
 int r2dm_axpby(float* y, const float* x, const float* noise, const float* ac, int batch, size_t per_sample,
                void* stream) {
   if (!y || !x || !noise || !ac) return fail(-1, "null argument");
-  CUDA_TRY(axpby_launch(x, noise, ac, y, batch, per_sample, static_cast<cudaStream_t>(stream)));
+  CUDA_TRY(axpby_launch(x, noise, ac, y, batch, per_sample, nullptr, 0, 1, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_axpby_table(float* y, const float* x, const float* noise, const float* table, const int* step_ptr,
+                     int rows_per_step, int row_batch_stride, int batch, size_t per_sample, void* stream) {
+  if (!y || !x || !noise || !table) return fail(-1, "null argument");
+  CUDA_TRY(axpby_launch(x, noise, table, y, batch, per_sample, step_ptr, rows_per_step, row_batch_stride,
+                        static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -380,35 +380,88 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
     @torch.inference_mode()
     def repaint(self, known, mask, num_steps: int, num_resample_steps: int = 1, jump_length: int = 1,
                 progress: bool = True, rng=None, return_all: bool = False):
-        """continuous_time.py:260-317 (RePaint, https://arxiv.org/abs/2201.09865); mask == 1 is known."""
+        """continuous_time.py:260-317 (RePaint, https://arxiv.org/abs/2201.09865); mask == 1 is known.
+
+        The (t, s) sequence of all reverse / re-noising steps is static, so like `sample` the loop runs
+        from precomputed tables: reverse steps (U-Net + update + known-region blend) and forward steps
+        (q_step re-noising) are two CUDA graphs driven by device-side counters.  Draw order per reverse
+        step is the reference's: known-region noise first, then the p_step noise."""
         assert num_resample_steps > 0
         assert jump_length > 0
         batch_size = known.shape[0]
-        known = L.f32c(known.to(self.device))
-        mask = L.f32c(mask.to(self.device).expand_as(known))
-        x_t = self.randn(batch_size, *self.sampling_shape, rng=rng, device=self.device)
-        steps = torch.linspace(1, 0, num_steps + 1)[None].repeat_interleave(batch_size, dim=0)
-        out = [x_t] if return_all else None
-        x_s = None
-        for i in tqdm(range(num_steps), desc="RePaint", leave=False, disable=not progress):
+        dev = self.device
+        known = L.f32c(known.to(dev))
+        mask = L.f32c(mask.to(dev).expand_as(known))
+        x = L.f32c(self.randn(batch_size, *self.sampling_shape, rng=rng, device=dev)).clone()
+        steps = torch.linspace(1, 0, num_steps + 1)
+        interp = torch.linspace(0, 1, jump_length + 1)
+        # ---- static schedule: 'p' = reverse step r[k] -> r[k+1]; 'q' = re-noise r[k] -> r[k-1]
+        prog, p_t, p_s, q_t, q_s = [], [], [], [], []
+        for i in range(num_steps):
             for j in range(num_resample_steps):
-                step_t, step_s = steps[:, [i]], steps[:, [i + 1]]
-                interp = torch.linspace(0, 1, jump_length + 1)
-                r_steps = step_t + interp[None] * (step_s - step_t)
-                x = x_t
-                for k in range(jump_length):   # t -> s, known region re-noised and blended in-kernel
-                    x = self.p_step(x, r_steps[:, k], r_steps[:, k + 1], rng=rng, _known=known, _mask=mask)
-                x_s = x
-                if return_all:
-                    out.append(x_s)
+                r = steps[i] + interp * (steps[i + 1] - steps[i])
+                for k in range(jump_length):
+                    prog.append("p"); p_t.append(r[k]); p_s.append(r[k + 1])
+                prog.append("out")
                 if (i == num_steps - 1) or (j == num_resample_steps - 1):
-                    x_t = x
                     break
-                x = x_s
-                for k in range(jump_length, 0, -1):   # s -> t
-                    x = self.q_step(x, r_steps[:, k - 1], r_steps[:, k], rng=rng)
-                x_t = x
-        return torch.stack(out) if return_all else x_s
+                for k in range(jump_length, 0, -1):
+                    prog.append("q"); q_t.append(r[k - 1]); q_s.append(r[k])
+        lam_pt, lam_ps = self._lam(torch.stack(p_t)), self._lam(torch.stack(p_s))
+        coef = continuous_coefficients(lam_pt, lam_ps, "ddpm", 0.0, self.objective)
+        a_s, s_s = _log_snr_to_alpha_sigma(lam_ps.double())
+        coef = torch.cat([coef, a_s[:, None], s_s[:, None]], dim=1)           # known_s = a_s known + s_s noise2
+        eng = self._engine()
+        lib = L.lib()
+        with torch.cuda.device(dev):
+            film = eng.cond_embed(lam_pt.to(dev))
+            coef = coef.to(device=dev, dtype=torch.float32).contiguous()
+            if q_t:
+                a_t, s_t = _log_snr_to_alpha_sigma(self._lam(torch.stack(q_t)).double())
+                a_q, s_q = _log_snr_to_alpha_sigma(self._lam(torch.stack(q_s)).double())
+                a_ts = a_t / a_q
+                qtab = torch.stack([a_ts, (s_t ** 2 - a_ts ** 2 * s_q ** 2).clamp(min=0).sqrt()], dim=1)
+                qtab = qtab.to(device=dev, dtype=torch.float32).contiguous()
+            pstep = torch.zeros(1, dtype=torch.int32, device=dev)
+            qstep = torch.zeros(1, dtype=torch.int32, device=dev)
+            pred, noise, noise2 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+            per = x[0].numel()
+
+            def reverse_step():
+                eng.forward_film(x, film, pred, step_ptr=pstep, rows_per_step=1, row_batch_stride=0)
+                self._update(x, x, pred, noise, coef, pstep, 1, 0, known, mask, noise2)
+                L.check(lib.r2dm_advance_step(L.ptr(pstep), 1, L.stream_ptr()))
+
+            def renoise_step():
+                L.check(lib.r2dm_axpby_table(L.ptr(x), L.ptr(x), L.ptr(noise), L.ptr(qtab), L.ptr(qstep), 1, 0,
+                                             batch_size, per, L.stream_ptr()), "r2dm_axpby_table")
+                L.check(lib.r2dm_advance_step(L.ptr(qstep), 1, L.stream_ptr()))
+
+            graphs = {"p": None, "q": None}
+            fns = {"p": reverse_step, "q": renoise_step}
+            seen = {"p": 0, "q": 0}
+            out = [x.clone()] if return_all else None
+            n_p = sum(1 for o in prog if o == "p")
+            for op in tqdm(prog, desc="RePaint", leave=False, disable=not progress):
+                if op == "out":
+                    if return_all:
+                        out.append(x.clone())
+                    continue
+                if op == "p":
+                    self.randn_like(x, rng=rng, out=noise2)     # q_step_from_x_0(known) draw
+                self.randn_like(x, rng=rng, out=noise)
+                if graphs[op] is not None:
+                    graphs[op].replay()
+                    continue
+                fns[op]()                                       # first occurrence runs eagerly
+                seen[op] += 1
+                if self.use_cuda_graph and n_p > 2 and seen[op] == 1:
+                    torch.cuda.current_stream().synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        fns[op]()
+                    graphs[op] = g
+        return torch.stack(out) if return_all else x
 
 
 # ------------------------------------------------------------------------------------- discrete
