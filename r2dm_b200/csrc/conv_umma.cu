@@ -130,6 +130,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __shared__ float stat_s[2][8][kNU][2];
   __shared__ float coef_s[2][kMaxCin];
   __shared__ float grp_s[2][kNU];
+  __shared__ __align__(16) float bias_s[NT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.tiles_total / gridDim.x);
@@ -152,6 +153,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) and the resident-weight preload below overlap the tail of the previous kernel; no
+  // activation / statistics / output address is touched before pdl_wait().
+  pdl_launch_dependents();
 
   auto decode = [&](int t, int& b, int& yt, int& xt, int& nt) {
     nt = t % p.ntiles; t /= p.ntiles;
@@ -170,6 +175,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES,
                     &wres_bar);
       }
+      pdl_wait();
       uint32_t it = 0;
       for (int t = t_begin; t < t_end; ++t) {
         int b, yt, xt, nt;
@@ -295,6 +301,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ operand transform
     if (p.xf.enabled) {
+      pdl_wait();
       const int tt = threadIdx.x - 128;                 // 0..127
       constexpr int TPP = 128 / Tr::PLANES;             // threads per channel plane
       const int my_plane = tt / TPP, tip = tt % TPP;
@@ -424,12 +431,19 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     const uint4* res = static_cast<const uint4*>(p.residual);
     uint4* out = static_cast<uint4*>(p.out);
     const int ethread = threadIdx.x - 256;
-    int j = 0;
+    pdl_wait();
+    int j = 0, cur_nt = -1;
     for (int t = t_begin; t < t_end; ++t, ++j) {
       int b, yt, xt, nt;
       decode(t, b, yt, xt, nt);
       const int n0 = nt * NT, x = xt * 128 + m, y0 = yt * HT;
       const int buf = j & 1;
+      if (nt != cur_nt) {   // bias of this N tile -> shared memory (once per CTA when ntiles == 1)
+        cur_nt = nt;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = ethread; i < NT; i += 256) bias_s[i] = p.bias[n0 + i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       // GroupNorm partial sums per 8-channel chunk of the columns this warp visits (compile-time
       // indexed registers); chunks are folded into statistics units once per tile
       constexpr int CCOLS = HT > 1 ? NT : NT / 2;       // columns visited by this warp
@@ -462,10 +476,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
           for (int h16 = 0; h16 < CB / 16; ++h16) tmem_ld16(tbase + r * NT + c0 + h16 * 16, v + h16 * 16);
           tmem_ld_wait();
-          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+          const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
           for (int i4 = 0; i4 < CB / 4; ++i4) {
-            const float4 bv = __ldg(bias4 + i4);
+            const float4 bv = bias4[i4];
             v[4 * i4] += bv.x; v[4 * i4 + 1] += bv.y; v[4 * i4 + 2] += bv.z; v[4 * i4 + 3] += bv.w;
           }
           if (p.out_nchw != nullptr) {
@@ -689,8 +703,15 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   }
   int grid = num_sms();
   if (grid > p.tiles_total) grid = p.tiles_total;
-  kern<<<grid, 512, smem, s>>>(p);
-  return cudaGetLastError();
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("R2DM_PDL"); pdl = e ? atoi(e) : 1; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 template <typename T>

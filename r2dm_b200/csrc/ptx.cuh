@@ -77,6 +77,11 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
                : "memory");
 }
 
+// programmatic dependent launch: wait until the previous kernel in the stream has completed and its
+// writes are visible / allow the next kernel to begin launching
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
