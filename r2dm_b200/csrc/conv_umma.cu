@@ -117,7 +117,7 @@ __device__ __forceinline__ float silu_from_half(float h) {
   return fmaf(h, th, h);
 }
 
-template <typename T, int NT, int HT, int TAPS, int KS>
+template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW>
 __global__ void __launch_bounds__(512, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
   using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
@@ -127,7 +127,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], xf_bar[kMaxStages];
   __shared__ uint64_t acc_full[2], acc_empty[2], wres_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float stat_s[2][8][kNU][2];
+  __shared__ float stat_w[2][8][NT / 8 > 0 ? NT / 8 : 1][2];   // [tile parity][epilogue warp][8-channel sub-chunk][sum, sumsq]
   __shared__ float coef_s[2][kMaxCin];
   __shared__ float grp_s[2][kNU];
   __shared__ __align__(16) float bias_s[NT];
@@ -153,6 +153,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && p.trace_cap >= 8) {
+    p.trace[p.trace_cap - 4] = static_cast<unsigned long long>(clock64());   // (clock, globaltimer) at start
+    p.trace[p.trace_cap - 3] = gtime();
+  }
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
   // prefetch) and the resident-weight preload below overlap the tail of the previous kernel; no
   // activation / statistics / output address is touched before pdl_wait().
@@ -420,14 +424,22 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ epilogue
+    // Compact on purpose: the column-chunk loop is NOT unrolled (the fully unrolled version was
+    // 96 KB of SASS and the eight epilogue warps stalled on instruction fetch).
     const int ew = warp - 8;            // 0..7
     const int q = ew & 3;               // TMEM lane quarter (must equal warp % 4)
     const int half = ew >> 2;           // which rows (HT > 1) or which column half (HT == 1)
     const int m = q * 32 + lane;
     const int Wp = p.W + 2;
     const int planes_out = p.cout_pad / CW;
-    constexpr int NUT = NT >= 8 * kNU ? kNU : (NT / 8 > 0 ? NT / 8 : 1);  // max units per tile
-    constexpr int CB = NT >= 32 ? 32 : 16;   // columns per TMEM load batch
+    const size_t plane_stride = static_cast<size_t>(p.H) * Wp;   // 16-byte units between channel planes
+    constexpr int CB = NT >= 32 ? 32 : 16;              // columns per chunk
+    constexpr int CCOLS = HT > 1 ? NT : NT / 2;         // columns visited by this warp
+    constexpr int NCHUNK = CCOLS / CB;
+    constexpr int NSUB = CB / 8;                        // 8-channel statistics sub-chunks per chunk
+    constexpr int RSTEP = HT > 1 ? 2 : 1;
+    const int r_begin = HT > 1 ? half : 0;
+    const int c_begin = HT > 1 ? 0 : half * (NT / 2);
     const uint4* res = static_cast<const uint4*>(p.residual);
     uint4* out = static_cast<uint4*>(p.out);
     const int ethread = threadIdx.x - 256;
@@ -437,82 +449,101 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       int b, yt, xt, nt;
       decode(t, b, yt, xt, nt);
       const int n0 = nt * NT, x = xt * 128 + m, y0 = yt * HT;
-      const int buf = j & 1;
+      const int buf = j & 1, par = j & 1;
       if (nt != cur_nt) {   // bias of this N tile -> shared memory (once per CTA when ntiles == 1)
         cur_nt = nt;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int i = ethread; i < NT; i += 256) bias_s[i] = p.bias[n0 + i];
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      // GroupNorm partial sums per 8-channel chunk of the columns this warp visits (compile-time
-      // indexed registers); chunks are folded into statistics units once per tile
-      constexpr int CCOLS = HT > 1 ? NT : NT / 2;       // columns visited by this warp
-      constexpr int NCH = CCOLS / 8 > 0 ? CCOLS / 8 : 1;
-      float sacc[NCH][2];
-#pragma unroll
-      for (int u = 0; u < NCH; ++u) { sacc[u][0] = 0.f; sacc[u][1] = 0.f; }
       mbar_wait_relaxed(&acc_full[buf], (j >> 1) & 1, 1000);
       tc_fence_after();
       if (ethread == 0) R2DM_TRACE(3, 3 * j);
       const uint32_t tbase = tmem + buf * Tr::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
-      constexpr int RSTEP = HT > 1 ? 2 : 1;
-      const int r_begin = HT > 1 ? half : 0;
-      const int c_begin = HT > 1 ? 0 : half * (NT / 2);
 #pragma unroll 1
-      for (int r = r_begin; r < HT; r += RSTEP) {
-        const int y = y0 + r;
-        if (y >= p.H) break;
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int c0 = c_begin + ch * CB;
+        float ssum[NSUB][2];
 #pragma unroll
-        for (int cb = 0; cb < CCOLS; cb += CB) {
-          const int c0 = c_begin + cb;
-          // residual prefetch (independent loads in flight while TMEM is read)
-          uint4 rr[CB / CW];
-          if (res != nullptr && p.out_nchw == nullptr) {
+        for (int u = 0; u < NSUB; ++u) { ssum[u][0] = 0.f; ssum[u][1] = 0.f; }
 #pragma unroll
-            for (int u = 0; u < CB / CW; ++u)
-              rr[u] = res[pt_index(b, planes_out, (n0 + c0) / CW + u, p.H, Wp, y, x + 1)];
-          }
-          float v[CB];
+        for (int r = r_begin; r < HT; r += RSTEP) {
+          const int y = y0 + r;
+          if (y < p.H) {
+            const size_t idx0 = pt_index(b, planes_out, (n0 + c0) / CW, p.H, Wp, y, x + 1);
+            // residual prefetch (independent loads in flight while TMEM is read)
+            uint4 rr[CB / CW];
+            if (!NCHW && res != nullptr) {
 #pragma unroll
-          for (int h16 = 0; h16 < CB / 16; ++h16) tmem_ld16(tbase + r * NT + c0 + h16 * 16, v + h16 * 16);
-          tmem_ld_wait();
-          const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c0);
-#pragma unroll
-          for (int i4 = 0; i4 < CB / 4; ++i4) {
-            const float4 bv = bias4[i4];
-            v[4 * i4] += bv.x; v[4 * i4 + 1] += bv.y; v[4 * i4 + 2] += bv.z; v[4 * i4 + 3] += bv.w;
-          }
-          if (p.out_nchw != nullptr) {
-#pragma unroll
-            for (int i = 0; i < CB; ++i) {
-              const int ch = n0 + c0 + i;
-              if (ch < p.cout)
-                p.out_nchw[((static_cast<size_t>(b) * p.cout + ch) * p.H + y) * p.W + x] = v[i] * p.scale;
+              for (int u = 0; u < CB / CW; ++u) rr[u] = res[idx0 + u * plane_stride];
             }
-            continue;
+            float v[CB];
+#pragma unroll
+            for (int h16 = 0; h16 < CB / 16; ++h16) tmem_ld16(tbase + r * NT + c0 + h16 * 16, v + h16 * 16);
+            tmem_ld_wait();
+            const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c0);
+#pragma unroll
+            for (int i4 = 0; i4 < CB / 4; ++i4) {
+              const float4 bv = bias4[i4];
+              v[4 * i4] += bv.x; v[4 * i4 + 1] += bv.y; v[4 * i4 + 2] += bv.z; v[4 * i4 + 3] += bv.w;
+            }
+            if constexpr (NCHW) {
+              float* dst = p.out_nchw + ((static_cast<size_t>(b) * p.cout + n0 + c0) * p.H + y) * p.W + x;
+              const size_t cstride = static_cast<size_t>(p.H) * p.W;
+#pragma unroll
+              for (int i = 0; i < CB; ++i)
+                if (n0 + c0 + i < p.cout) dst[i * cstride] = v[i] * p.scale;
+            } else {
+#pragma unroll
+              for (int u = 0; u < CB / CW; ++u) {
+                const size_t idx = idx0 + u * plane_stride;
+                float o[CW];
+#pragma unroll
+                for (int i = 0; i < CW; ++i) o[i] = v[u * CW + i];
+                if (res != nullptr) {
+                  float rv[CW];
+                  Elem<T>::unpack(rr[u], rv);
+#pragma unroll
+                  for (int i = 0; i < CW; ++i) o[i] += rv[i];
+                }
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < CW; ++i) { o[i] *= p.scale; s1 += o[i]; s2 = fmaf(o[i], o[i], s2); }
+                ssum[(u * CW) / 8][0] += s1;
+                ssum[(u * CW) / 8][1] += s2;
+                const uint4 pk = Elem<T>::pack(o);
+                out[idx] = pk;
+                if (x == 0) out[idx + p.W] = pk;              // xp = W+1 mirrors pixel 0
+                if (x == p.W - 1) out[idx - p.W] = pk;        // xp = 0 mirrors pixel W-1
+              }
+            }
+          }
+        }
+        if (!NCHW && p.stats != nullptr) {
+          // warp totals of the 2*NSUB partial sums with a transposing butterfly (NSUB*2 - 1 + 2
+          // shuffles instead of 5 per value): afterwards value i lives in the lanes whose bits
+          // [4:..] spell i; lane with (lane & (32/(2*NSUB) - 1)) == 0 stores it
+          float vals[2 * NSUB];
+#pragma unroll
+          for (int u = 0; u < NSUB; ++u) { vals[2 * u] = ssum[u][0]; vals[2 * u + 1] = ssum[u][1]; }
+          constexpr int LOGV = NSUB == 4 ? 3 : (NSUB == 2 ? 2 : 1);   // log2(2 * NSUB)
+#pragma unroll
+          for (int rd = 0; rd < LOGV; ++rd) {
+            const int nv = (2 * NSUB) >> rd, off = 16 >> rd;
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < nv / 2; ++i) {
+              const float send = upper ? vals[i] : vals[i + nv / 2];
+              const float keep = upper ? vals[i + nv / 2] : vals[i];
+              vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
           }
 #pragma unroll
-          for (int u = 0; u < CB / CW; ++u) {
-            const int cl = c0 + u * CW;  // channel within the N tile
-            const size_t idx = pt_index(b, planes_out, (n0 + cl) / CW, p.H, Wp, y, x + 1);
-            float o[CW];
-#pragma unroll
-            for (int i = 0; i < CW; ++i) o[i] = v[u * CW + i];
-            if (res != nullptr) {
-              float rv[CW];
-              Elem<T>::unpack(rr[u], rv);
-#pragma unroll
-              for (int i = 0; i < CW; ++i) o[i] += rv[i];
-            }
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < CW; ++i) { o[i] *= p.scale; s1 += o[i]; s2 = fmaf(o[i], o[i], s2); }
-            sacc[(cb + u * CW) / 8][0] += s1;
-            sacc[(cb + u * CW) / 8][1] += s2;
-            const uint4 pk = Elem<T>::pack(o);
-            out[idx] = pk;
-            if (x == 0) out[idx + p.W] = pk;              // xp = W+1 mirrors pixel 0
-            if (x == p.W - 1) out[idx - p.W] = pk;        // xp = 0 mirrors pixel W-1
+          for (int off = 16 >> LOGV; off > 0; off >>= 1) vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
+          constexpr int LPV = 32 / (2 * NSUB);          // lanes per value
+          if ((lane & (LPV - 1)) == 0) {
+            const int vi = lane / LPV;                  // = 2 * sub + k
+            stat_w[par][ew][(c0 >> 3) + (vi >> 1)][vi & 1] = vals[0];
           }
         }
       }
@@ -521,33 +552,21 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       if (ethread == 0) R2DM_TRACE(3, 3 * j + 1);
-      if (p.stats != nullptr) {
-        // fold chunk sums into statistics units (unit_ch = 8 << k channels), then across lanes/warps
-        const int par = j & 1;
-        const int cpu = p.unit_ch >> 3;                  // chunks per unit (power of two)
-        const int units_w = NCH / cpu;                   // units visited by this warp
-        const int unit0_w = (c_begin >> 3) / cpu;        // first unit of this warp within the tile
-#pragma unroll
-        for (int u = 0; u < NUT; ++u) {
-          if (u < units_w) {
-            float a = 0.f, qv = 0.f;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-              if ((c >> (p.unit_shift - 3)) == u) { a += sacc[c][0]; qv += sacc[c][1]; }
-            a = warp_sum(a); qv = warp_sum(qv);
-            if (lane == 0) { stat_s[par][ew][unit0_w + u][0] = a; stat_s[par][ew][unit0_w + u][1] = qv; }
-          }
-        }
+      if (!NCHW && p.stats != nullptr) {
+        // fold 8-channel sub-chunks into statistics units (unit_ch = 8 << k channels) and across warps
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int units_here = NT / p.unit_ch;
         if (ethread < units_here * 2) {
           const int u = ethread >> 1, k = ethread & 1;
+          const int cpu = p.unit_ch >> 3;                // sub-chunks per unit (power of two)
           float tot = 0.f;
-          // HT > 1: every warp saw all units; HT == 1: warps 0-3 saw the lower half, 4-7 the upper
+          for (int sc = u * cpu; sc < (u + 1) * cpu; ++sc) {
+            // HT > 1: every warp visited all columns; HT == 1: warps 0-3 the lower half, 4-7 the upper
 #pragma unroll
-          for (int w = 0; w < 8; ++w) {
-            const bool has = HT > 1 ? true : ((w >> 2) == (u >= units_here / 2 ? 1 : 0)) || units_here == 1;
-            if (has) tot += stat_s[par][w][u][k];
+            for (int w = 0; w < 8; ++w) {
+              const bool has = HT > 1 ? true : (w >> 2) == (sc >= NT / 16 ? 1 : 0);
+              if (has) tot += stat_w[par][w][sc][k];
+            }
           }
           const int unit = n0 / p.unit_ch + u;
           const int slot = yt * p.xtiles + xt;
@@ -558,6 +577,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && p.trace_cap >= 8) {
+    p.trace[p.trace_cap - 2] = static_cast<unsigned long long>(clock64());   // ... and at the end: SM clock rate
+    p.trace[p.trace_cap - 1] = gtime();
+  }
   if (warp == 2) tmem_dealloc<Tr::TMEM_COLS>(tmem);
 }
 
@@ -642,10 +665,11 @@ void conv_set_trace(unsigned long long* buf, int cap) { g_trace = buf; g_trace_c
 constexpr int kSmemBudget = 216 * 1024;     // dynamic smem per CTA (227 KB limit minus ~9.5 KB static)
 constexpr int kWresMaxBytes = 80 * 1024;    // keep the filter bank resident below this size
 
-template <typename T, int NT, int HT, int TAPS, int KS>
+template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW = false>
 static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
-  auto kern = conv_umma_kernel<T, NT, HT, TAPS, KS>;
+  auto kern = conv_umma_kernel<T, NT, HT, TAPS, KS, NCHW>;
+  if ((l.out_nchw != nullptr) != NCHW) return cudaErrorInvalidConfiguration;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
@@ -721,7 +745,8 @@ static cudaError_t dispatch(const ConvLaunch& l, cudaStream_t s) {
     if (l.nt == 64 && l.ht == 2) return launch_one<T, 64, 2, 9, 1>(l, s);
     if (l.nt == 128 && l.ht == 2) return launch_one<T, 128, 2, 9, 1>(l, s);
     if (l.nt == 128 && l.ht == 1) return launch_one<T, 128, 1, 9, 1>(l, s);
-    if (l.nt == 16 && l.ht == 4) return launch_one<T, 16, 4, 9, 1>(l, s);
+    if (l.nt == 16 && l.ht == 4)
+      return l.out_nchw ? launch_one<T, 16, 4, 9, 1, true>(l, s) : launch_one<T, 16, 4, 9, 1>(l, s);
   } else if (l.taps == 1) {
     if (l.nt == 64 && l.ht == 2) return launch_one<T, 64, 2, 1, 4>(l, s);
     if (l.nt == 128 && l.ht == 2) return launch_one<T, 128, 2, 1, 4>(l, s);
