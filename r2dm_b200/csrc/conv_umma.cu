@@ -7,7 +7,7 @@
 // nn.GroupNorm / ops.AdaGN + nn.SiLU that feed them (efficient_unet.py:72-81,99-106; ops.py:176-200).
 //
 // Persistent kernel: one CTA per SM walks a contiguous range of output tiles (HT rows x 128 pixels
-// x NT output channels).  Warp roles (512 threads):
+// x NT output channels).  Warp roles (640 threads):
 //   warp 0      producer.  Per pipeline stage (KCH input channels) one 5-D TMA box load brings the
 //               halo tile [(HT+2) x 130 px] of those channels into shared memory (planar-16 layout,
 //               common.cuh) and one bulk copy brings the pre-packed weights of all taps for those
@@ -18,11 +18,11 @@
 //               once per tile, not once per tap).  Accumulators: 2 x (HT x NT) fp32 TMEM columns,
 //               double buffered so the epilogue of tile j overlaps the MMAs of tile j+1.
 //   warp 2      TMEM allocator.
-//   warps 4-7   operand transform (optional).  Applies y = silu(a_c x + d_c) in place on the freshly
+//   warps 4-11  operand transform (optional; two groups of four warps on alternating stages).  Applies y = silu(a_c x + d_c) in place on the freshly
 //               landed stage, where (a_c, d_c) fold the GroupNorm statistics left by the producer
 //               kernel, the affine / FiLM parameters and the normalisation; rows outside the image
 //               stay zero (the conv's zero padding applies to the *normalised* tensor).
-//   warps 8-15  epilogue.  tcgen05.ld -> + bias (+ residual) -> * scale -> GroupNorm partial sums
+//   warps 12-19 epilogue.  tcgen05.ld -> + bias (+ residual) -> * scale -> GroupNorm partial sums
 //               for the consumer -> bf16/fp32 planar-16 store (incl. the wrap halo columns), or fp32
 //               NCHW store for the network output.
 // Elevation borders come from TMA out-of-bounds zero fill; the azimuth wrap from the halo columns.
@@ -36,6 +36,8 @@
 namespace r2dm {
 
 constexpr int kMaxStages = 8;
+constexpr int kConvThreads = 640;   // 4 control warps + 2 x 4 transform warps + 8 epilogue warps
+constexpr int kEpiWarp0 = 12;       // first epilogue warp (multiple of 4: TMEM lane quarter = warp % 4)
 constexpr int kMaxCin = 1024;
 
 struct XformParams {
@@ -118,7 +120,7 @@ __device__ __forceinline__ float silu_from_half(float h) {
 }
 
 template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
   using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
   constexpr int CW = Tr::CW;
@@ -302,11 +304,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         umma_commit(&acc_full[buf]);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < kEpiWarp0) {
     // ------------------------------------------------------------------ operand transform
+    // Two groups of four warps; group g transforms the pipeline stages with (global index % 2) == g,
+    // so two stages are in flight and the XU (tanh) pipe of every SM sub-partition always has a
+    // second warp to issue from while the first waits on shared memory.
     if (p.xf.enabled) {
       pdl_wait();
-      const int tt = threadIdx.x - 128;                 // 0..127
+      const int grp = (warp - 4) >> 2;                  // 0 / 1
+      const int t256 = threadIdx.x - 128;               // 0..255 over both groups
+      const int tt = t256 & 127;                        // 0..127 within the group
       constexpr int TPP = 128 / Tr::PLANES;             // threads per channel plane
       const int my_plane = tt / TPP, tip = tt % TPP;
       const int Ctot = p.xf.C0 + p.xf.C1;
@@ -317,10 +324,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         int b, yt, xt, nt;
         decode(t, b, yt, xt, nt);
         if (b != cur_b) {
-          // ---- fold statistics + affine/FiLM into per-channel (a, d) for image b
+          // ---- fold statistics + affine/FiLM into per-channel (a, d) for image b (all 8 warps; the
+          // first barrier also guarantees that nobody still reads the previous image's table)
           cur_b = b;
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          {
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (grp == 0) {
             const int g = tt >> 4, l16 = tt & 15;        // 16 threads per group (groups == 8)
             double s1 = 0.0, s2 = 0.0;
             const int lo = g * gsize, hi_c = lo + gsize;
@@ -351,10 +359,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               double var = s2 / cnt - mean * mean;
               if (var < 0.0) var = 0.0;
               grp_s[0][g] = static_cast<float>(mean);
-              grp_s[1][g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.xf.eps)));
+              grp_s[1][g] = rsqrtf(static_cast<float>(var) + p.xf.eps);
             }
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 2, 256;" ::: "memory");
           const float* fl = nullptr;
           if (p.xf.film != nullptr) {
             const int row = (p.xf.step_ptr ? *p.xf.step_ptr : 0) * p.xf.rows_per_step + b * p.xf.row_batch_stride;
@@ -362,7 +370,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           }
           // with the fast SiLU the coefficients produce h = t/2 directly
           const float fold = (p.xf.silu && sizeof(T) == 2) ? 0.5f : 1.f;
-          for (int c = tt; c < Ctot; c += 128) {
+          for (int c = t256; c < Ctot; c += 256) {
             const int g = c / gsize;
             const float ga = fl ? 1.f + fl[c] : p.xf.gamma[c];
             const float be = fl ? fl[Ctot + c] : p.xf.beta[c];
@@ -370,12 +378,13 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             coef_s[0][c] = a * fold;
             coef_s[1][c] = (be - grp_s[0][g] * a) * fold;
           }
-          asm volatile("bar.sync 2, 128;" ::: "memory");
+          asm volatile("bar.sync 2, 256;" ::: "memory");
         }
         const int y_first = TAPS == 9 ? yt * HT - 1 : yt * HT;   // image row of tile row 0
         const int row_lo = max(0, -y_first), row_hi = min(Tr::AROWS, p.H - y_first);
         const int n_units = (row_hi - row_lo) * Tr::APITCH;
         for (int ks = 0; ks < p.nk; ++ks, ++it) {
+          if ((it & 1u) != static_cast<uint32_t>(grp)) continue;
           const int st = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
           float ca[CW], cd[CW];
@@ -387,46 +396,48 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             cd[i] = ok ? coef_s[1][c0 + i] : 0.f;
           }
           mbar_wait_relaxed(&full_bar[st], ph, 500);
-          if (tt == 0) R2DM_TRACE(2, 2 * it);
+          if (t256 == 0) R2DM_TRACE(2, 2 * it);
           const uint32_t sbase = smem_u32(smem_ring + static_cast<size_t>(st) * p.stage_bytes +
                                           my_plane * Tr::A_PLANE_BYTES) + row_lo * Tr::APITCH * 16;
-          if (c0 < Ctot && (p.xf.debug == 0 || p.xf.debug == 3)) {
-            // batches of XB units: all loads first, then the math, then the stores (the plain
-            // pointer version compiled into a serial load -> math -> store chain per unit)
+          auto xform_unit = [&](uint4 raw) {
+            float v[CW];
+            Elem<T>::unpack(raw, v);
+#pragma unroll
+            for (int k = 0; k < CW; ++k) {
+              const float tv = fmaf(v[k], ca[k], cd[k]);
+              v[k] = p.xf.silu ? (sizeof(T) == 2 ? silu_from_half(tv) : silu_f(tv)) : tv;
+            }
+            return Elem<T>::pack_mma(v);
+          };
+          if (c0 < Ctot && p.xf.debug == 0) {
+            // full batches of XB units per thread: all loads first, then the math, then the stores;
+            // the remainder (n_units is not a multiple of XB * TPP) goes one unit at a time so that no
+            // XU-pipe slots are spent on padding
             constexpr int XB = 4;
-            for (int i0 = tip; i0 < n_units; i0 += XB * TPP) {
+            int i0 = tip;
+            for (; i0 + (XB - 1) * TPP < n_units; i0 += XB * TPP) {
               uint4 raw[XB];
 #pragma unroll
-              for (int u = 0; u < XB; ++u)
-                if (i0 + u * TPP < n_units) raw[u] = lds128(sbase + (i0 + u * TPP) * 16);
+              for (int u = 0; u < XB; ++u) raw[u] = lds128(sbase + (i0 + u * TPP) * 16);
 #pragma unroll
-              for (int u = 0; u < XB; ++u) {
-                float v[CW];
-                Elem<T>::unpack(raw[u], v);
+              for (int u = 0; u < XB; ++u) raw[u] = xform_unit(raw[u]);
 #pragma unroll
-                for (int k = 0; k < CW; ++k) {
-                  const float tv = fmaf(v[k], ca[k], cd[k]);
-                  v[k] = (p.xf.silu && p.xf.debug != 3) ? (sizeof(T) == 2 ? silu_from_half(tv) : silu_f(tv)) : tv;
-                }
-                raw[u] = Elem<T>::pack_mma(v);
-              }
-#pragma unroll
-              for (int u = 0; u < XB; ++u)
-                if (i0 + u * TPP < n_units) sts128(sbase + (i0 + u * TPP) * 16, raw[u]);
+              for (int u = 0; u < XB; ++u) sts128(sbase + (i0 + u * TPP) * 16, raw[u]);
             }
+            for (; i0 < n_units; i0 += TPP) sts128(sbase + i0 * 16, xform_unit(lds128(sbase + i0 * 16)));
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&xf_bar[st]);
-          if (tt == 0) R2DM_TRACE(2, 2 * it + 1);
+          if (t256 == 0) R2DM_TRACE(2, 2 * it + 1);
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue
     // Compact on purpose: the column-chunk loop is NOT unrolled (the fully unrolled version was
     // 96 KB of SASS and the eight epilogue warps stalled on instruction fetch).
-    const int ew = warp - 8;            // 0..7
+    const int ew = warp - kEpiWarp0;    // 0..7
     const int q = ew & 3;               // TMEM lane quarter (must equal warp % 4)
     const int half = ew >> 2;           // which rows (HT > 1) or which column half (HT == 1)
     const int m = q * 32 + lane;
@@ -442,7 +453,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     const int c_begin = HT > 1 ? 0 : half * (NT / 2);
     const uint4* res = static_cast<const uint4*>(p.residual);
     uint4* out = static_cast<uint4*>(p.out);
-    const int ethread = threadIdx.x - 256;
+    const int ethread = threadIdx.x - kEpiWarp0 * 32;
     pdl_wait();
     int j = 0, cur_nt = -1;
     for (int t = t_begin; t < t_end; ++t, ++j) {
@@ -730,7 +741,7 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   static int pdl = -1;
   if (pdl < 0) { const char* e = getenv("R2DM_PDL"); pdl = e ? atoi(e) : 1; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
