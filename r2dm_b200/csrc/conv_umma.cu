@@ -71,7 +71,7 @@ struct ConvParams {
   float scale;
   int stages, stage_bytes, wres;  // smem ring depth / stride; weights resident in smem
   int debug;  // developer ablation knob (R2DM_CONV_DEBUG): 1 no epilogue stores, 2 no MMA issue, 4 no TMA
-  unsigned long long* trace;  // developer timeline (r2dm_debug_set_trace): [4 roles][cap] globaltimer ns of CTA 0
+  unsigned long long* trace;  // developer timeline (r2dm_debug_set_trace): [5 roles][cap] clock64 of CTA 0
   int trace_cap;
 };
 
@@ -85,12 +85,13 @@ struct ConvTraits {
   static constexpr int A_PLANE_BYTES = AROWS * APITCH * 16;
   static constexpr int A_BYTES = PLANES * A_PLANE_BYTES;
   static constexpr int A_BYTES_AL = (A_BYTES + 127) / 128 * 128;
-  // FUSE (3x3, NT = 64): the three vertical taps of one horizontal offset are ONE MMA with N = 192:
+  // FUSE (3x3, NT = 64; NT = 128 fuses two taps, N = 256): the vertical taps of one horizontal offset
+  // are ONE MMA with N = 192:
   // the shifted A view of input row i feeds output rows i-1, i, i+1 (adjacent accumulator column
   // blocks), because a 128x64x16 MMA cannot go below ~60 cycles (53 % of the tensor pipe, measured
   // with tools/probe_mma_rate.cu) while N >= 128 runs at full rate.  Weights are then packed as
   // [kx][plane][ky descending][co] so that any contiguous ky range is a contiguous row range of B.
-  static constexpr bool FUSE = (TAPS == 9 && NT == 64);
+  static constexpr bool FUSE = (TAPS == 9 && (NT == 64 || (NT == 128 && HT <= 2)));
   static constexpr int B_PLANE_BYTES = (FUSE ? 3 : 1) * NT * 16;
   static constexpr int B_TAP_BYTES = PLANES * B_PLANE_BYTES;          // one tap (or one kx block)
   static constexpr int B_BYTES = (FUSE ? 3 : TAPS) * B_TAP_BYTES;
@@ -110,7 +111,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define R2DM_TRACE(role, idx)                                                          \
   do {                                                                                 \
     if (p.trace != nullptr && blockIdx.x == 0 && (idx) < p.trace_cap)                  \
-      p.trace[(role) * p.trace_cap + (idx)] = gtime();                                 \
+      p.trace[(role) * p.trace_cap + (idx)] = static_cast<unsigned long long>(clock64()); \
   } while (0)
 
 __device__ __forceinline__ float silu_from_half(float h) {
@@ -396,7 +397,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             cd[i] = ok ? coef_s[1][c0 + i] : 0.f;
           }
           mbar_wait_relaxed(&full_bar[st], ph, 500);
-          if (t256 == 0) R2DM_TRACE(2, 2 * it);
+          if (tt == 0) R2DM_TRACE(grp ? 4 : 2, 2 * it);
           const uint32_t sbase = smem_u32(smem_ring + static_cast<size_t>(st) * p.stage_bytes +
                                           my_plane * Tr::A_PLANE_BYTES) + row_lo * Tr::APITCH * 16;
           auto xform_unit = [&](uint4 raw) {
@@ -429,7 +430,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&xf_bar[st]);
-          if (t256 == 0) R2DM_TRACE(2, 2 * it + 1);
+          if (tt == 0) R2DM_TRACE(grp ? 4 : 2, 2 * it + 1);
         }
       }
     }
@@ -816,7 +817,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin, int cin_pad,
                              int cout_pad, void* dst, cudaStream_t s) {
   const int planes = 2 * ks_for(taps);
-  const int fuse = (taps == 9 && nt == 64) ? 1 : 0;
+  const int fuse = (taps == 9 && (nt == 64 || nt == 128)) ? 1 : 0;
   const size_t total = static_cast<size_t>(taps) * cin_pad * cout_pad;
   const int grid = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   if (dtype == kBF16)

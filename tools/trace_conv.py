@@ -24,7 +24,7 @@ def run():
 for _ in range(2):
     run()
 cap = 4096
-buf = torch.zeros(4, cap, dtype=torch.int64, device="cuda")
+buf = torch.zeros(5, cap, dtype=torch.int64, device="cuda")
 L.lib().r2dm_debug_set_trace(buf.data_ptr(), cap)
 run()
 torch.cuda.synchronize()
@@ -34,12 +34,13 @@ c0, g0, c1, g1 = (int(v) for v in t[0, cap - 4:].tolist())
 t[0, cap - 4:] = 0
 print(f"shape {Cin}->{Cout} @{H}x{W} gn={gn}: CTA0 lifetime {(g1 - g0) / 1e3:.1f} us, {c1 - c0} SM cycles -> "
       f"{(c1 - c0) / max(g1 - g0, 1) * 1e3:.0f} MHz effective SM clock")
+mhz = (c1 - c0) / max(g1 - g0, 1) * 1e3
 t0 = int(t[t > 0].min())
-names = ["producer(issue)", "mma(wait,commit)", "xform(wait,arrive)", "epilogue(full,release,-)"]
-for r in range(4):
-    ev = [(int(v) - t0) / 1e3 for v in t[r].tolist() if v > 0]
+names = ["producer(issue)", "mma(wait,commit)", "xform0(wait,arrive)", "epilogue(full,release,-)", "xform1(wait,arrive)"]
+for r in range(5):
+    ev = [(int(v) - t0) / mhz for v in t[r].tolist() if v > 0]   # SM cycles -> us
     print(names[r], len(ev), "events, us:", " ".join(f"{e:.2f}" for e in ev[:48]))
-    if r in (1, 2) and len(ev) >= 4:
+    if r in (1, 2, 4) and len(ev) >= 4:
         busy = [ev[i + 1] - ev[i] for i in range(0, len(ev) - 1, 2)]
         wait = [ev[i + 2] - ev[i + 1] for i in range(0, len(ev) - 2, 2)]
         print(f"   mean busy (wait-done -> signal) {sum(busy) / len(busy):.3f} us, mean gap (signal -> next wait-done) "
