@@ -210,7 +210,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // the whole warp runs this loop convergently; one elected lane issues (see umma_f16_warp)
+    {
       const uint32_t idesc = make_idesc(128, NT, Elem<T>::kFmt);
       const uint32_t idesc2 = make_idesc(128, 2 * NT <= 256 ? 2 * NT : NT, Elem<T>::kFmt);
       const uint32_t idesc3 = make_idesc(128, 3 * NT <= 256 ? 3 * NT : NT, Elem<T>::kFmt);
@@ -231,7 +232,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           const uint32_t ph = (it / p.stages) & 1;
           mbar_wait(p.xf.enabled ? &xf_bar[st] : &full_bar[st], ph);
           tc_fence_after();
-          R2DM_TRACE(1, 2 * it);
+          if (lane == 0) R2DM_TRACE(1, 2 * it);
           const uint32_t sa = smem_u32(smem_ring + static_cast<size_t>(st) * p.stage_bytes);
           const uint32_t sb = p.wres ? smem_u32(smem_w) + static_cast<uint32_t>(ks) * Tr::B_BYTES : sa + Tr::A_BYTES_AL;
           // low descriptor words of the stage bases; every operand below is base + compile-time
@@ -258,8 +259,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                       const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
                                              (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky) * NT * 16) >> 4));
                       if (p.debug & 2) continue;
-                      if (Elem<T>::kFmt == 2) umma_tf32(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
-                      else umma_f16(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
+                      if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
+                      else umma_f16_warp(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
                     }
                   }
                 } else {
@@ -273,8 +274,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                                            (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky_hi) * NT * 16) >> 4));
                     const uint32_t idn = nrows == 3 ? idesc3 : (nrows == 2 ? idesc2 : idesc);
                     if (p.debug & 2) continue;
-                    if (Elem<T>::kFmt == 2) umma_tf32(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
-                    else umma_f16(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
+                    if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
+                    else umma_f16_warp(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
                   }
                 }
               }
@@ -293,16 +294,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                   const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) | (b_lo0 + b_add);
                   const uint32_t acc = (ks > 0 || tap > 0 || kk > 0) ? 1u : 0u;
                   if (p.debug & 2) continue;
-                  if (Elem<T>::kFmt == 2) umma_tf32(dbase + r * NT, adesc, bdesc, idesc, acc);
-                  else umma_f16(dbase + r * NT, adesc, bdesc, idesc, acc);
+                  if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r * NT, adesc, bdesc, idesc, acc);
+                  else umma_f16_warp(dbase + r * NT, adesc, bdesc, idesc, acc);
                 }
               }
             }
           }
-          umma_commit(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
-          R2DM_TRACE(1, 2 * it + 1);
+          umma_commit_warp(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
+          if (lane == 0) R2DM_TRACE(1, 2 * it + 1);
         }
-        umma_commit(&acc_full[buf]);
+        umma_commit_warp(&acc_full[buf]);
       }
     }
   } else if (warp >= 4 && warp < kEpiWarp0) {
@@ -473,7 +474,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       if (ethread == 0) R2DM_TRACE(3, 3 * j);
       const uint32_t tbase = tmem + buf * Tr::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int ch = 0; ch < NCHUNK; ++ch) {
+      for (int ch = 0; ch < ((p.debug & 1) ? 0 : NCHUNK); ++ch) {
         const int c0 = c_begin + ch * CB;
         float ssum[NSUB][2];
 #pragma unroll
@@ -487,7 +488,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             uint4 rr[CB / CW];
             if (!NCHW && res != nullptr) {
 #pragma unroll
-              for (int u = 0; u < CB / CW; ++u) rr[u] = res[idx0 + u * plane_stride];
+              for (int u = 0; u < CB / CW; ++u) rr[u] = (p.debug & 8) ? make_uint4(0u, 0u, 0u, 0u) : res[idx0 + u * plane_stride];
             }
             float v[CB];
 #pragma unroll

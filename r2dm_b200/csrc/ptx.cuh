@@ -156,6 +156,40 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-convergent variants: the WHOLE warp executes the call with identical (warp-uniform) operands and
+// one elected lane issues.  Issued from a divergent `if (lane == 0)` branch the compiler cannot prove the
+// operands uniform and wraps every UTCHMMA in an ELECT / BRA.U.ANY loop (~13 instructions, ~60 cycles
+// of a single thread per MMA); here the descriptors are computed on the uniform datapath.
+__device__ __forceinline__ void umma_f16_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
 // Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
