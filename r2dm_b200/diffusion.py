@@ -138,6 +138,7 @@ class GaussianDiffusion(nn.Module):
             assert hasattr(self.model, "in_channels")
             self.sampling_shape = (self.model.in_channels, *sampling_resolution)
         self.use_cuda_graph = True
+        self.graph_steps = 8   # denoising steps captured per CUDA graph in sample()
         self._graphs = {}
         self.setup_parameters()
         self.register_buffer("_dummy", torch.tensor([]))
@@ -217,52 +218,84 @@ class GaussianDiffusion(nn.Module):
 
     def _run_table(self, x, conds, coefs, rng, return_all, progress, desc, draw_noise):
         """Shared hot loop: N steps over precomputed (cond, coefficient) tables with a device-side
-        step counter; one CUDA graph per (batch, precision) replayed every step."""
+        step counter.  The loop runs as CUDA graphs of `graph_steps` denoising steps; graphs and their
+        static buffers (state, prediction, noise, tables) are cached on this object and reused by later
+        calls with the same batch size, so a call costs N step replays and nothing else."""
         eng = self._engine()
         dev = x.device
         N = conds.numel()
+        B = x.shape[0]
         with torch.cuda.device(dev):
-            film = eng.cond_embed(conds.to(dev))
-            coef = coefs.to(device=dev, dtype=torch.float32).contiguous()
-            step = torch.zeros(1, dtype=torch.int32, device=dev)
-            x = L.f32c(x).clone()
-            pred = torch.empty_like(x)
-            noise = torch.empty_like(x)
-            out = [x.clone()] if return_all else None
             lib = L.lib()
+            K = 1 if return_all else max(1, int(getattr(self, "graph_steps", 8)))
+            ncoef = coefs.shape[1]
+            key = (B, K, ncoef, self._clip(), tuple(x.shape[1:]))
+            eng.bind(B)
+            st = getattr(self, "_loop_state", None)
+            if (st is None or st["key"] != key or st["eng"] is not eng or st["epoch"] != eng.bind_epoch
+                    or st["film"].shape[0] < N):
+                st = {
+                    "key": key, "eng": eng, "epoch": eng.bind_epoch,
+                    "x": torch.empty((B,) + tuple(x.shape[1:]), device=dev, dtype=torch.float32),
+                    "pred": torch.empty((B,) + tuple(x.shape[1:]), device=dev, dtype=torch.float32),
+                    "noise": torch.zeros((K, B) + tuple(x.shape[1:]), device=dev, dtype=torch.float32),
+                    "film": torch.zeros(max(N, 256), eng.film_width, device=dev, dtype=torch.float32),
+                    "coef": torch.zeros(max(N, 256), ncoef, device=dev, dtype=torch.float32),
+                    "step": torch.zeros(1, dtype=torch.int32, device=dev),
+                    "graphs": {}, "warm": False,
+                }
+                self._loop_state = st
+            xs, pred, noise, step = st["x"], st["pred"], st["noise"], st["step"]
+            st["film"][:N].copy_(eng.cond_embed(conds.to(dev)))
+            st["coef"][:N].copy_(coefs.to(device=dev, dtype=torch.float32))
+            xs.copy_(L.f32c(x))
+            step.zero_()
+            if not draw_noise:
+                noise.zero_()
+            out = [xs.clone()] if return_all else None
 
-            def one_step():
-                eng.forward_film(x, film, pred, step_ptr=step, rows_per_step=1, row_batch_stride=0)
-                self._update(x, x, pred, noise, coef, step, 1, 0)
+            def one_step(k=0):
+                eng.forward_film(xs, st["film"], pred, step_ptr=step, rows_per_step=1, row_batch_stride=0)
+                self._update(xs, xs, pred, noise[k], st["coef"], step, 1, 0)
                 L.check(lib.r2dm_advance_step(L.ptr(step), 1, L.stream_ptr()))
 
-            graph = None
-            start = 0
-            if self.use_cuda_graph and N > 2:
-                # the first step runs eagerly (lazy kernel attribute setup), then capture
+            def draw(n):
                 if draw_noise:
-                    self.randn_like(x, rng=rng, out=noise)
+                    for k in range(n):
+                        self.randn_like(xs, rng=rng, out=noise[k])
+
+            def capture(n):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for k in range(n):
+                        one_step(k)
+                return g   # capture does not execute: the device counter is unchanged
+
+            use_graph = self.use_cuda_graph and N > 2
+            done = 0
+            bar = tqdm(total=N, desc=desc, leave=False, disable=not progress)
+            while done < N:
+                warmup = use_graph and not st["warm"]
+                n = 1 if warmup else min(K, N - done)
+                draw(n)
+                if warmup:
+                    # very first step of this cache entry runs eagerly (lazy kernel attribute setup)
+                    one_step(0)
+                    torch.cuda.current_stream().synchronize()
+                    st["warm"] = True
+                elif use_graph:
+                    if n not in st["graphs"]:
+                        st["graphs"][n] = capture(n)
+                    st["graphs"][n].replay()
                 else:
-                    noise.zero_()
-                one_step()
+                    for k in range(n):
+                        one_step(k)
+                done += n
+                bar.update(n)
                 if return_all:
-                    out.append(x.clone())
-                start = 1
-                torch.cuda.current_stream().synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    one_step()
-                # capture does not execute: the counter still points at step 1
-            for _ in tqdm(range(start, N), desc=desc, leave=False, disable=not progress):
-                if draw_noise:
-                    self.randn_like(x, rng=rng, out=noise)
-                if graph is not None:
-                    graph.replay()
-                else:
-                    one_step()
-                if return_all:
-                    out.append(x.clone())
-        return torch.stack(out) if return_all else x
+                    out.append(xs.clone())
+            bar.close()
+        return torch.stack(out) if return_all else xs.clone()
 
 
 # ------------------------------------------------------------------------------------- continuous

@@ -282,6 +282,7 @@ class UNetEngine:
         self.film_width = self.lib.r2dm_film_width(self.h)
         self._ws: Dict[int, torch.Tensor] = {}
         self._bound_batch = None
+        self.bind_epoch = 0   # bumped whenever the workspace binding (and with it every captured pointer) changes
         self._zero_step = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     @staticmethod
@@ -312,6 +313,7 @@ class UNetEngine:
             L.check(self.lib.r2dm_bind_workspace(self.h, self._aligned(ws, 1024), nbytes, batch, L.stream_ptr()),
                     "bind workspace")
         self._bound_batch = batch
+        self.bind_epoch += 1
 
     @property
     def launches_per_forward(self) -> int:
