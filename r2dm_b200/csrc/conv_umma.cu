@@ -469,6 +469,17 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int i = ethread; i < NT; i += 256) bias_s[i] = p.bias[n0 + i];
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      if (!NCHW && res != nullptr) {
+        // pull the residual tile into L2 while the MMAs of this tile run (one 128-byte line per request)
+        constexpr int SEGS = HT * (NT / CW);             // (row, plane) segments of 128 px = 2 KB
+        for (int l = ethread; l < SEGS * 16; l += 256) {
+          const int seg = l >> 4, row = seg / (NT / CW), pl = seg % (NT / CW);
+          if (y0 + row < p.H) {
+            const uint4* a = res + pt_index(b, planes_out, n0 / CW + pl, p.H, Wp, y0 + row, xt * 128 + 1) + (l & 15) * 8;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
+        }
+      }
       mbar_wait_relaxed(&acc_full[buf], (j >> 1) & 1, 1000);
       tc_fence_after();
       if (ethread == 0) R2DM_TRACE(3, 3 * j);

@@ -254,6 +254,12 @@ struct Builder {
     if (w.taps == 9) l.ht = (w.nt == 128) ? (a.H >= 2 ? 2 : 1) : (a.H % 4 == 0 ? 4 : (a.H >= 2 ? 2 : 1));
     else l.ht = a.H >= 2 ? 2 : 1;
     if (w.nt == 16 && l.ht != 4) l.ht = 4;
+    // low-resolution levels: with two-row tiles fewer than half of the 148 SMs would get a tile, so
+    // halve the tile (the persistent grid then covers twice as many SMs with half the K loop each)
+    if (w.taps == 9 && w.nt == 128 && l.ht == 2) {
+      const long long tiles = static_cast<long long>(a.B) * (a.H / 2) * (a.W / 128) * (w.cout_pad / 128);
+      if (tiles <= 74) l.ht = 1;
+    }
     l.in0 = a;
     if (in1 >= 0) l.in1 = T(in1);
     l.cin_pad = w.cin_pad; l.cout = w.cout; l.cout_pad = w.cout_pad;
