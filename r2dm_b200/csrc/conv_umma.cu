@@ -183,15 +183,14 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     &wres_bar);
       }
       pdl_wait();
-      uint32_t it = 0;
+      uint32_t it = 0, ph = 0;
+      int st = 0;   // ring slot / phase advance incrementally (no division per stage)
       for (int t = t_begin; t < t_end; ++t) {
         int b, yt, xt, nt;
         decode(t, b, yt, xt, nt);
         const int x0 = xt * 128, y0 = yt * HT;
         const uint8_t* wsrc = static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(nt) * p.nk * Tr::B_BYTES;
-        for (int ks = 0; ks < p.nk; ++ks, ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int ks = 0; ks < p.nk; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
           mbar_wait_relaxed(&empty_bar[st], ph ^ 1, 2000);
           uint8_t* sa = smem_ring + static_cast<size_t>(st) * p.stage_bytes;
           if (p.debug & 4) { mbar_arrive(&full_bar[st]); continue; }
@@ -220,16 +219,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       const uint32_t a_lo_const = static_cast<uint32_t>(Tr::A_PLANE_BYTES >> 4) << 16;
       const uint32_t b_lo_const = static_cast<uint32_t>(Tr::B_PLANE_BYTES >> 4) << 16;
       if (p.wres) mbar_wait(&wres_bar, 0);
-      uint32_t it = 0;
+      uint32_t it = 0, ph = 0;
+      int st = 0;
       int j = 0;
       for (int t = t_begin; t < t_end; ++t, ++j) {
         const int buf = j & 1;
         mbar_wait(&acc_empty[buf], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t dbase = tmem + buf * Tr::ACC_COLS;
-        for (int ks = 0; ks < p.nk; ++ks, ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
+        for (int ks = 0; ks < p.nk; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
           mbar_wait(p.xf.enabled ? &xf_bar[st] : &full_bar[st], ph);
           tc_fence_after();
           if (lane == 0) R2DM_TRACE(1, 2 * it);
@@ -240,7 +238,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           const uint32_t a_lo0 = a_lo_const | ((sa >> 4) & 0x3FFFu);
           const uint32_t b_lo0 = b_lo_const | ((sb >> 4) & 0x3FFFu);
           constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
-          if constexpr (Tr::FUSE) {
+          if (p.debug & 2) {
+            // developer ablation: no MMAs issued
+          } else if constexpr (Tr::FUSE) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
@@ -258,7 +258,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                                              (a_lo0 + a_k + static_cast<uint32_t>(((r + ky) * Tr::APITCH * 16) >> 4));
                       const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
                                              (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky) * NT * 16) >> 4));
-                      if (p.debug & 2) continue;
                       if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
                       else umma_f16_warp(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
                     }
@@ -273,7 +272,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
                                            (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky_hi) * NT * 16) >> 4));
                     const uint32_t idn = nrows == 3 ? idesc3 : (nrows == 2 ? idesc2 : idesc);
-                    if (p.debug & 2) continue;
                     if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
                     else umma_f16_warp(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
                   }
@@ -293,7 +291,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                   const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) | (a_lo0 + a_add);
                   const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) | (b_lo0 + b_add);
                   const uint32_t acc = (ks > 0 || tap > 0 || kk > 0) ? 1u : 0u;
-                  if (p.debug & 2) continue;
                   if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r * NT, adesc, bdesc, idesc, acc);
                   else umma_f16_warp(dbase + r * NT, adesc, bdesc, idesc, acc);
                 }
@@ -320,7 +317,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       const int my_plane = tt / TPP, tip = tt % TPP;
       const int Ctot = p.xf.C0 + p.xf.C1;
       const int gsize = Ctot / p.xf.groups;
-      uint32_t it = 0;
+      uint32_t it = 0, ph = 0;
+      int st = 0;
       int cur_b = -1;
       for (int t = t_begin; t < t_end; ++t) {
         int b, yt, xt, nt;
@@ -385,10 +383,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         const int y_first = TAPS == 9 ? yt * HT - 1 : yt * HT;   // image row of tile row 0
         const int row_lo = max(0, -y_first), row_hi = min(Tr::AROWS, p.H - y_first);
         const int n_units = (row_hi - row_lo) * Tr::APITCH;
-        for (int ks = 0; ks < p.nk; ++ks, ++it) {
+        for (int ks = 0; ks < p.nk; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
           if ((it & 1u) != static_cast<uint32_t>(grp)) continue;
-          const int st = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
           float ca[CW], cd[CW];
           const int c0 = (ks * Tr::PLANES + my_plane) * CW;
 #pragma unroll
