@@ -240,7 +240,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "images_per_step": B * world, "denoising_steps": NUM_STEPS,
                    "sampler": "ddim eta=0", "l2": "working set per step >> L2 (each of the 256 forwards streams "
-                   "~1.4 GB of activations; no explicit flush)", "cuda_graph": True},
+                   "~1.4 GB of activations; no explicit flush)", "cuda_graph": True,
+                   "graph_steps": int(getattr(ddpm, "graph_steps", 1))},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": 8 * B * world,
                 "d2h_bytes_per_step": B * world * 5 * 64 * 1024 * 4},
         "gpu_launches": launches,
