@@ -247,34 +247,39 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               for (int kk = 0; kk < KS; ++kk) {
                 const uint32_t a_k = static_cast<uint32_t>((kk * 2 * Tr::A_PLANE_BYTES + kx * 16) >> 4);
                 const uint32_t b_k = static_cast<uint32_t>((kx * Tr::B_TAP_BYTES + kk * 2 * Tr::B_PLANE_BYTES) >> 4);
-                if (ks == 0 && kx == 0 && kk == 0) {
-                  // first touch of the accumulators: per-tap N = 64 MMAs so that the accumulate
-                  // flag can be cleared per output row
+                // First touch of the accumulators (ks = kx = kk = 0): the MMAs are issued in an order in
+                // which the first one(s) cover a partition of the output rows, so those clear the
+                // accumulators (accumulate = 0) and every other MMA accumulates: input row
+                // min(2, HT-1) feeds rows 0..min(2, HT-1), and for HT = 4 input row 5 feeds row 3 alone.
+                static_assert(HT <= 4, "first-touch order assumes at most four output rows per tile");
+                constexpr int IR_A = HT - 1 < 2 ? HT - 1 : 2;
+                constexpr int IR_B = HT - 1 > IR_A ? HT + 1 : -1;
+                const bool first = ks == 0 && kx == 0 && kk == 0;
 #pragma unroll
-                  for (int r = 0; r < HT; ++r) {
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                      const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) |
-                                             (a_lo0 + a_k + static_cast<uint32_t>(((r + ky) * Tr::APITCH * 16) >> 4));
-                      const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
-                                             (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky) * NT * 16) >> 4));
-                      if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
-                      else umma_f16_warp(dbase + r * NT, adesc, bdesc, idesc, ky > 0);
+                for (int idx = 0; idx < HT + 2; ++idx) {
+                  // issue order: IR_A, IR_B (if any), then the remaining input rows ascending
+                  int ir = idx;
+                  if (idx == 0) ir = IR_A;
+                  else if (IR_B >= 0 && idx == 1) ir = IR_B;
+                  else {
+                    int k = idx - (IR_B >= 0 ? 2 : 1);   // k-th row of the remaining ones
+                    ir = 0;
+                    for (int c = 0; c < HT + 2; ++c) {
+                      if (c == IR_A || c == IR_B) continue;
+                      if (k == 0) { ir = c; break; }
+                      --k;
                     }
                   }
-                } else {
-#pragma unroll
-                  for (int ir = 0; ir < HT + 2; ++ir) {
-                    const int r_lo = ir - 2 > 0 ? ir - 2 : 0, r_hi = ir < HT - 1 ? ir : HT - 1;
-                    const int ky_hi = ir - r_lo, nrows = r_hi - r_lo + 1;
-                    const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) |
-                                           (a_lo0 + a_k + static_cast<uint32_t>((ir * Tr::APITCH * 16) >> 4));
-                    const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
-                                           (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky_hi) * NT * 16) >> 4));
-                    const uint32_t idn = nrows == 3 ? idesc3 : (nrows == 2 ? idesc2 : idesc);
-                    if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
-                    else umma_f16_warp(dbase + r_lo * NT, adesc, bdesc, idn, 1u);
-                  }
+                  const int r_lo = ir - 2 > 0 ? ir - 2 : 0, r_hi = ir < HT - 1 ? ir : HT - 1;
+                  const int ky_hi = ir - r_lo, nrows = r_hi - r_lo + 1;
+                  const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) |
+                                         (a_lo0 + a_k + static_cast<uint32_t>((ir * Tr::APITCH * 16) >> 4));
+                  const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
+                                         (b_lo0 + b_k + static_cast<uint32_t>(((2 - ky_hi) * NT * 16) >> 4));
+                  const uint32_t idn = nrows == 3 ? idesc3 : (nrows == 2 ? idesc2 : idesc);
+                  const uint32_t acc = (first && (ir == IR_A || ir == IR_B)) ? 0u : 1u;
+                  if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r_lo * NT, adesc, bdesc, idn, acc);
+                  else umma_f16_warp(dbase + r_lo * NT, adesc, bdesc, idn, acc);
                 }
               }
             }
