@@ -257,8 +257,10 @@ struct Builder {
     // low-resolution levels: with two-row tiles fewer than half of the 148 SMs would get a tile, so
     // halve the tile (the persistent grid then covers twice as many SMs with half the K loop each)
     if (w.taps == 9 && w.nt == 128 && l.ht == 2) {
-      const long long tiles = static_cast<long long>(a.B) * (a.H / 2) * (a.W / 128) * (w.cout_pad / 128);
-      if (tiles <= 74) l.ht = 1;
+      // (decided per image, never from the batch size: the accumulation order depends on the tile
+      //  shape and results must not depend on the batch composition)
+      const int tiles_per_image = (a.H / 2) * (a.W / 128) * (w.cout_pad / 128);
+      if (tiles_per_image <= 9) l.ht = 1;
     }
     l.in0 = a;
     if (in1 >= 0) l.in1 = T(in1);
