@@ -332,6 +332,25 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           // ---- fold statistics + affine/FiLM into per-channel (a, d) for image b (all 8 warps; the
           // first barrier also guarantees that nobody still reads the previous image's table)
           cur_b = b;
+          if (t256 == 0 && it == 0) R2DM_TRACE(4, 0);   // statistics fold begins
+          // affine / FiLM parameters of this thread's channels: loaded first so that their latency
+          // overlaps the statistics loads (this fold sits on the critical path of every launch)
+          const float* fl = nullptr;
+          if (p.xf.film != nullptr) {
+            const int row = (p.xf.step_ptr ? *p.xf.step_ptr : 0) * p.xf.rows_per_step + b * p.xf.row_batch_stride;
+            fl = p.xf.film + static_cast<size_t>(row) * p.xf.film_stride + p.xf.film_off;
+          }
+          constexpr int CPT = kMaxCin / 256;             // channels per thread
+          float ga_r[CPT], be_r[CPT];
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int c = t256 + k * 256;
+            ga_r[k] = 0.f; be_r[k] = 0.f;
+            if (c < Ctot) {
+              ga_r[k] = fl ? 1.f + fl[c] : p.xf.gamma[c];
+              be_r[k] = fl ? fl[Ctot + c] : p.xf.beta[c];
+            }
+          }
           asm volatile("bar.sync 2, 256;" ::: "memory");
           if (grp == 0) {
             const int g = tt >> 4, l16 = tt & 15;        // 16 threads per group (groups == 8)
@@ -348,8 +367,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 const int unit_ch = Cs / kNU;
                 const int u0 = (a - off) / unit_ch, u1 = (e - off) / unit_ch;
                 const int n = (u1 - u0) * sl;
-                const float* st = stp + (static_cast<size_t>(b) * kNU + u0) * sl * 2;
-                for (int i = l16; i < n; i += 16) { s1 += st[2 * i]; s2 += st[2 * i + 1]; }
+                const float2* st2 = reinterpret_cast<const float2*>(stp + (static_cast<size_t>(b) * kNU + u0) * sl * 2);
+                // four independent loads in flight per thread, fp32 partial sums of at most four
+                // tile sums each, folded in double
+                int i = l16;
+                for (; i + 48 < n; i += 64) {
+                  const float2 v0 = st2[i], v1 = st2[i + 16], v2 = st2[i + 32], v3 = st2[i + 48];
+                  s1 += (static_cast<double>(v0.x) + v1.x) + (static_cast<double>(v2.x) + v3.x);
+                  s2 += (static_cast<double>(v0.y) + v1.y) + (static_cast<double>(v2.y) + v3.y);
+                }
+                for (; i < n; i += 16) { const float2 v = st2[i]; s1 += v.x; s2 += v.y; }
               }
               off += Cs;
             }
@@ -368,22 +395,20 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             }
           }
           asm volatile("bar.sync 2, 256;" ::: "memory");
-          const float* fl = nullptr;
-          if (p.xf.film != nullptr) {
-            const int row = (p.xf.step_ptr ? *p.xf.step_ptr : 0) * p.xf.rows_per_step + b * p.xf.row_batch_stride;
-            fl = p.xf.film + static_cast<size_t>(row) * p.xf.film_stride + p.xf.film_off;
-          }
           // with the fast SiLU the coefficients produce h = t/2 directly
           const float fold = (p.xf.silu && sizeof(T) == 2) ? 0.5f : 1.f;
-          for (int c = t256; c < Ctot; c += 256) {
-            const int g = c / gsize;
-            const float ga = fl ? 1.f + fl[c] : p.xf.gamma[c];
-            const float be = fl ? fl[Ctot + c] : p.xf.beta[c];
-            const float a = grp_s[1][g] * ga;
-            coef_s[0][c] = a * fold;
-            coef_s[1][c] = (be - grp_s[0][g] * a) * fold;
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) {
+            const int c = t256 + k * 256;
+            if (c < Ctot) {
+              const int g = c / gsize;
+              const float a = grp_s[1][g] * ga_r[k];
+              coef_s[0][c] = a * fold;
+              coef_s[1][c] = (be_r[k] - grp_s[0][g] * a) * fold;
+            }
           }
           asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (t256 == 0 && it == 0) R2DM_TRACE(4, 1);   // coefficient table ready
         }
         const int y_first = TAPS == 9 ? yt * HT - 1 : yt * HT;   // image row of tile row 0
         const int row_lo = max(0, -y_first), row_hi = min(Tr::AROWS, p.H - y_first);

@@ -32,6 +32,9 @@ L.lib().r2dm_debug_set_trace(None, 0)
 t = buf.cpu()
 c0, g0, c1, g1 = (int(v) for v in t[0, cap - 4:].tolist())
 t[0, cap - 4:] = 0
+first = int(t[t > 0].min())
+print(f"kernel start -> first traced event: {(first - c0) / ((c1 - c0) / max(g1 - g0, 1) * 1e3):.2f} us; last event -> kernel end: "
+      f"{(c1 - int(t.max())) / ((c1 - c0) / max(g1 - g0, 1) * 1e3):.2f} us")
 print(f"shape {Cin}->{Cout} @{H}x{W} gn={gn}: CTA0 lifetime {(g1 - g0) / 1e3:.1f} us, {c1 - c0} SM cycles -> "
       f"{(c1 - c0) / max(g1 - g0, 1) * 1e3:.0f} MHz effective SM clock")
 mhz = (c1 - c0) / max(g1 - g0, 1) * 1e3
