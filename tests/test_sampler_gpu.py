@@ -69,6 +69,30 @@ def test_sample_graph_equals_eager(ddpm):
     assert torch.equal(a, b)
 
 
+def test_sample_multi_step_graph_cache(ddpm):
+    """sample() replays cached CUDA graphs of `graph_steps` steps: the result must not depend on the chunk
+    size, on whether the cache is cold or warm, on calls with other step counts / batch sizes in between,
+    and `return_all` must still deliver every intermediate state (N + 1 entries, x_T first)."""
+    N = 11
+    ddpm.graph_steps = 1
+    ddpm._loop_state = None
+    ref = ddpm.sample(batch_size=B, num_steps=N, progress=False, rng=cpu_rng(3), mode="ddim", ddim_eta=0.3)
+    for k in (4, 8):                                    # 11 steps = 1 eager + 4+4+2 / 8+2 (remainder graphs)
+        ddpm.graph_steps = k
+        ddpm._loop_state = None
+        cold = ddpm.sample(batch_size=B, num_steps=N, progress=False, rng=cpu_rng(3), mode="ddim", ddim_eta=0.3)
+        ddpm.sample(batch_size=B, num_steps=5, progress=False, rng=cpu_rng(4), mode="ddpm")       # other N, other mode
+        ddpm.sample(batch_size=1, num_steps=3, progress=False, rng=cpu_rng(4)[:1], mode="ddpm")   # other batch: rebind
+        warm = ddpm.sample(batch_size=B, num_steps=N, progress=False, rng=cpu_rng(3), mode="ddim", ddim_eta=0.3)
+        torch.cuda.synchronize()
+        assert torch.equal(cold, ref), f"graph_steps={k}: cold cache differs from single-step graphs"
+        assert torch.equal(warm, ref), f"graph_steps={k}: warm cache differs from single-step graphs"
+    traj = ddpm.sample(batch_size=B, num_steps=N, progress=False, rng=cpu_rng(3), mode="ddim", ddim_eta=0.3,
+                       return_all=True)
+    assert traj.shape[0] == N + 1 and torch.equal(traj[-1], ref)
+    ddpm.graph_steps = 8
+
+
 def test_sample_cuda_generators_batch_split(ddpm):
     """rng = per-sample CUDA generators (utils/inference.py:113-114): sample i depends on seed i only."""
     import r2dm_b200 as R
