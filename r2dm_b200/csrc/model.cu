@@ -106,9 +106,17 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
   return static_cast<int>(m->raws.size()) - 1;
 }
 
-int pick_nt(int taps, int cout) {
-  (void)taps;
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("R2DM_PAIR"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
+// N tile: 256 selects the CTA-pair kernel (bf16 3x3 convolutions with a multiple of 256 output channels
+// on tensors with an even number of rows), else 128 / 64 / 16 output channels per single-CTA tile
+int pick_nt(int taps, int cout, int dtype, bool even_rows) {
   if (cout <= 16) return 16;
+  if (taps == 9 && dtype == kBF16 && cout % 256 == 0 && even_rows && pair_enabled()) return 256;
   return cout % 128 == 0 ? 128 : 64;
 }
 
@@ -116,7 +124,7 @@ int add_conv(r2dm_model* m, const std::string& name, int taps, int cin, int cout
   ConvW c;
   c.name = name;
   c.taps = taps; c.cin = cin; c.cout = cout;
-  c.nt = pick_nt(taps, cout);
+  c.nt = pick_nt(taps, cout, m->dtype, m->cfg.height % 16 == 0);   // every level then has an even height
   c.cin_pad = round_up(cin, conv_stage_channels(m->dtype, taps));
   c.cout_pad = round_up(cout, c.nt);
   c.w_off = m->arena_bytes;
@@ -251,7 +259,7 @@ struct Builder {
     ConvLaunch& l = op.conv;
     memset(&l, 0, sizeof(l));
     l.dtype = m->dtype; l.taps = w.taps; l.nt = w.nt;
-    if (w.taps == 9) l.ht = (w.nt == 128) ? (a.H >= 2 ? 2 : 1) : (a.H % 4 == 0 ? 4 : (a.H >= 2 ? 2 : 1));
+    if (w.taps == 9) l.ht = (w.nt == 256) ? 1 : (w.nt == 128) ? (a.H >= 2 ? 2 : 1) : (a.H % 4 == 0 ? 4 : (a.H >= 2 ? 2 : 1));
     else l.ht = a.H >= 2 ? 2 : 1;
     if (w.nt == 16 && l.ht != 4) l.ht = 4;
     // low-resolution levels: with two-row tiles fewer than half of the 148 SMs would get a tile, so
@@ -811,10 +819,10 @@ int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const floa
   ConvLaunch l;
   memset(&l, 0, sizeof(l));
   l.dtype = dtype; l.taps = taps;
-  l.nt = pick_nt(taps, Cout);
+  l.nt = pick_nt(taps, Cout, dtype, H % 2 == 0);
   l.cin_pad = round_up(Cin, conv_stage_channels(dtype, taps));
   l.cout = Cout; l.cout_pad = round_up(Cout, l.nt);
-  if (taps == 9) l.ht = (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
+  if (taps == 9) l.ht = (l.nt == 256) ? 1 : (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
   else l.ht = H >= 2 ? 2 : 1;
   if (l.nt == 16 && l.ht != 4) return fail(-1, "small-N conv needs H %% 4 == 0");
   l.in0 = make_pt(sc, dtype, B, l.cin_pad, H, W, 0);
@@ -853,11 +861,11 @@ int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, con
   ConvLaunch l;
   memset(&l, 0, sizeof(l));
   l.dtype = dtype; l.taps = taps;
-  l.nt = pick_nt(taps, Cout);
+  l.nt = pick_nt(taps, Cout, dtype, H % 2 == 0);
   l.cin_pad = round_up(Cin, conv_stage_channels(dtype, taps));
   if (l.cin_pad != Cin) return fail(-1, "Cin must be a multiple of the stage K (%d)", conv_stage_channels(dtype, taps));
   l.cout = Cout; l.cout_pad = round_up(Cout, l.nt);
-  if (taps == 9) l.ht = (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
+  if (taps == 9) l.ht = (l.nt == 256) ? 1 : (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
   else l.ht = H >= 2 ? 2 : 1;
   PT probe; probe.B = B; probe.C = Cin; probe.H = H; probe.W = W;
   l.in0 = make_pt(sc, dtype, B, Cin, H, W, tensor_stats_slots(dtype, probe));

@@ -46,6 +46,8 @@ CONV_CASES = [
     (2, 128, 64, 4, 128, 1, False),
     (1, 512, 1536, 2, 128, 1, False),
     (1, 256, 256, 2, 128, 1, True),
+    (2, 128, 256, 4, 256, 3, True),     # >= 256 output channels, even height: CTA-pair kernel (bf16)
+    (1, 64, 512, 2, 128, 3, False),     # two 256-channel N tiles, one row pair
 ]
 
 
@@ -124,7 +126,8 @@ def test_attention_core(case, dtype):
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp32"])
 @pytest.mark.parametrize("case", [(2, 64, 64, 8, 256, 3, False), (1, 128, 64, 4, 128, 3, True),
-                                  (2, 256, 128, 2, 128, 3, True), (1, 512, 1536, 4, 128, 1, False)])
+                                  (2, 256, 128, 2, 128, 3, True), (1, 512, 1536, 4, 128, 1, False),
+                                  (2, 256, 256, 4, 128, 3, True), (1, 128, 512, 6, 256, 3, False)])   # CTA-pair kernel
 def test_fused_groupnorm_conv(case, dtype):
     """The network's fused form: GroupNorm/AdaGN (+SiLU) applied to the operand tile inside the conv.
     The normalised activations are rounded to the operand type (bf16 / tf32) before the MMA, so the
