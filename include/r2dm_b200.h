@@ -138,6 +138,10 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
  * returns channel count via *C_out etc.  Names: "in_conv", "<block>", "<block>.rb<i>". */
 /* developer aid: record a per-role globaltimer timeline of CTA 0 of subsequent conv launches into
  * buf[4][cap] (uint64 ns; roles: producer, MMA, transform, epilogue); NULL disables. */
+/* Process-wide kernel-selection options, read when a model is created / an r2dm_op_* call is planned.
+ *   "pair" = 1: 3x3 convolutions with a multiple of 256 output channels (bf16, even height) run on the
+ *               thread-block-cluster kernel (two CTAs, tcgen05.mma.cta_group::2); default 0. */
+int r2dm_set_option(const char* name, int value);
 int r2dm_debug_set_trace(void* buf, int cap);
 int r2dm_debug_tensor(r2dm_handle h, const char* name, float* out, int* C, int* H, int* W, void* stream);
 

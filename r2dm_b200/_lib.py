@@ -77,6 +77,7 @@ _SIGS = {
                                    C.c_size_t, _P]),
     "r2dm_op_attention": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P,
                                     C.c_size_t, _P]),
+    "r2dm_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "r2dm_debug_set_trace": (C.c_int, [_P, C.c_int]),
     "r2dm_debug_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), _P]),

@@ -106,10 +106,12 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
   return static_cast<int>(m->raws.size()) - 1;
 }
 
+// CTA-pair kernel for >= 256 output channels: off by default (measured 12 % slower than the single-CTA
+// kernel in round 1); R2DM_PAIR=1 or r2dm_set_option("pair", 1) selects it
+static int g_pair = -1;
 static bool pair_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("R2DM_PAIR"); v = e ? atoi(e) : 1; }
-  return v != 0;
+  if (g_pair < 0) { const char* e = getenv("R2DM_PAIR"); g_pair = e ? atoi(e) : 0; }
+  return g_pair != 0;
 }
 
 // N tile: 256 selects the CTA-pair kernel (bf16 3x3 convolutions with a multiple of 256 output channels
@@ -949,6 +951,11 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
   }
   CUDA_TRY(unpack_nchw(dtype, out, y, 0, E, s));
   return 0;
+}
+
+int r2dm_set_option(const char* name, int value) {
+  if (name && std::string(name) == "pair") { g_pair = value ? 1 : 0; return 0; }
+  return fail(-1, "unknown option %s", name ? name : "(null)");
 }
 
 int r2dm_debug_set_trace(void* buf, int cap) {

@@ -46,8 +46,8 @@ CONV_CASES = [
     (2, 128, 64, 4, 128, 1, False),
     (1, 512, 1536, 2, 128, 1, False),
     (1, 256, 256, 2, 128, 1, True),
-    (2, 128, 256, 4, 256, 3, True),     # >= 256 output channels, even height: CTA-pair kernel (bf16)
-    (1, 64, 512, 2, 128, 3, False),     # two 256-channel N tiles, one row pair
+    (2, 128, 256, 4, 256, 3, True),
+    (1, 64, 512, 2, 128, 3, False),
 ]
 
 
@@ -127,7 +127,7 @@ def test_attention_core(case, dtype):
 @pytest.mark.parametrize("dtype", ["bf16", "fp32"])
 @pytest.mark.parametrize("case", [(2, 64, 64, 8, 256, 3, False), (1, 128, 64, 4, 128, 3, True),
                                   (2, 256, 128, 2, 128, 3, True), (1, 512, 1536, 4, 128, 1, False),
-                                  (2, 256, 256, 4, 128, 3, True), (1, 128, 512, 6, 256, 3, False)])   # CTA-pair kernel
+                                  (2, 256, 256, 4, 128, 3, True), (1, 128, 512, 6, 256, 3, False)])
 def test_fused_groupnorm_conv(case, dtype):
     """The network's fused form: GroupNorm/AdaGN (+SiLU) applied to the operand tile inside the conv.
     The normalised activations are rounded to the operand type (bf16 / tf32) before the MMA, so the
@@ -155,3 +155,40 @@ def test_fused_groupnorm_conv(case, dtype):
     e = rel_l2(y, ref)
     tol = 6e-3 if dtype == "bf16" else 1e-3
     assert e <= tol, f"fused gn+conv {case}[{dtype}]: l2-rel {e:.3e} > {tol}"
+
+
+# ------------------------------------------------------------------------------------------ CTA pairs
+@pytest.fixture
+def pair_kernel():
+    """Select the thread-block-cluster kernel (two CTAs, tcgen05.mma.cta_group::2) for 3x3 convolutions
+    with a multiple of 256 output channels; off by default."""
+    from r2dm_b200 import _lib
+    _lib.check(_lib.lib().r2dm_set_option(b"pair", 1), "set_option")
+    yield
+    _lib.check(_lib.lib().r2dm_set_option(b"pair", 0), "set_option")
+
+
+@pytest.mark.parametrize("case", [(2, 128, 256, 4, 256, 3, True), (1, 64, 512, 2, 128, 3, False),
+                                  (3, 256, 256, 8, 128, 3, True)])
+def test_conv_cta_pair(pair_kernel, case):
+    test_conv(case, "bf16")
+
+
+@pytest.mark.parametrize("case", [(2, 256, 256, 4, 128, 3, True), (1, 128, 512, 6, 256, 3, False),
+                                  (2, 512, 512, 2, 128, 3, True)])
+def test_fused_groupnorm_conv_cta_pair(pair_kernel, case):
+    test_fused_groupnorm_conv(case, "bf16")
+
+
+def test_cta_pair_matches_single_cta_kernel(pair_kernel):
+    """Same inputs through both kernels: identical products, different summation order only."""
+    from r2dm_b200 import _lib, ops
+    g = torch.Generator().manual_seed(5)
+    x = _round_to(torch.randn(2, 256, 8, 256, generator=g), "bf16").cuda()
+    w = _round_to(torch.randn(256, 256, 3, 3, generator=g) / 48.0, "bf16").cuda()
+    gm, bt = (1 + 0.1 * torch.randn(256, generator=g)).cuda(), (0.1 * torch.randn(256, generator=g)).cuda()
+    y_pair = ops.gn_conv2d(x, w, None, gamma=gm, beta=bt, dtype="bf16")
+    _lib.check(_lib.lib().r2dm_set_option(b"pair", 0), "set_option")
+    y_single = ops.gn_conv2d(x, w, None, gamma=gm, beta=bt, dtype="bf16")
+    torch.cuda.synchronize()
+    assert rel_l2(y_pair, y_single) < 2e-3
