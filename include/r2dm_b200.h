@@ -140,7 +140,9 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
  * buf[4][cap] (uint64 ns; roles: producer, MMA, transform, epilogue); NULL disables. */
 /* Process-wide kernel-selection options, read when a model is created / an r2dm_op_* call is planned.
  *   "pair" = 1: 3x3 convolutions with a multiple of 256 output channels (bf16, even height) run on the
- *               thread-block-cluster kernel (two CTAs, tcgen05.mma.cta_group::2); default 0. */
+ *               thread-block-cluster kernel (two CTAs, tcgen05.mma.cta_group::2, one row x 256 channels per CTA);
+ *          = 2: every 3x3 convolution with a multiple of 128 output channels (height a multiple of 4) runs on
+ *               its two-rows x 128-channels variant; default 0 (single-CTA kernels). */
 int r2dm_set_option(const char* name, int value);
 int r2dm_debug_set_trace(void* buf, int cap);
 int r2dm_debug_tensor(r2dm_handle h, const char* name, float* out, int* C, int* H, int* W, void* stream);

@@ -73,6 +73,7 @@ struct ConvParams {
   int debug;  // developer ablation knob (R2DM_CONV_DEBUG): 1 no epilogue stores, 2 no MMA issue, 4 no TMA
   unsigned long long* trace;  // developer timeline (r2dm_debug_set_trace): [5 roles][cap] clock64 of CTA 0
   int trace_cap;
+  unsigned trace_block;   // CTA whose roles are traced (R2DM_TRACE_BLOCK, default 0)
 };
 
 template <typename T, int NT, int HT, int TAPS, int KS>
@@ -110,7 +111,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define R2DM_TRACE(role, idx)                                                          \
   do {                                                                                 \
-    if (p.trace != nullptr && blockIdx.x == 0 && (idx) < p.trace_cap)                  \
+    if (p.trace != nullptr && blockIdx.x == p.trace_block && (idx) < p.trace_cap)      \
       p.trace[(role) * p.trace_cap + (idx)] = static_cast<unsigned long long>(clock64()); \
   } while (0)
 
@@ -156,7 +157,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && p.trace_cap >= 8) {
+  if (p.trace != nullptr && blockIdx.x == p.trace_block && threadIdx.x == 0 && p.trace_cap >= 8) {
     p.trace[p.trace_cap - 4] = static_cast<unsigned long long>(clock64());   // (clock, globaltimer) at start
     p.trace[p.trace_cap - 3] = gtime();
   }
@@ -627,7 +628,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && p.trace_cap >= 8) {
+  if (p.trace != nullptr && blockIdx.x == p.trace_block && threadIdx.x == 0 && p.trace_cap >= 8) {
     p.trace[p.trace_cap - 2] = static_cast<unsigned long long>(clock64());   // ... and at the end: SM clock rate
     p.trace[p.trace_cap - 1] = gtime();
   }
@@ -644,24 +645,32 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 // B bytes from local shared memory and no taps have to be fused.  Only the leader (rank 0) issues MMAs:
 //   full_bar / empty_bar / acc_full : local to each CTA (TMA completion; multicast tcgen05.commit)
 //   xf_bar / acc_empty              : the LEADER's, arrived on remotely by the peer's warps
-constexpr int kPairStages = 4;
+// Two shapes: <HT = 1, NP = 256> (one row x 256 channels per CTA, four ring slots) and <HT = 2, NP = 128>
+// (two rows x 128 channels per CTA; a slot is only 35 KB because each CTA holds 64 of the 128 weight rows,
+// so the ring is six slots deep - the stage hand-offs of this kernel are latency bound).
+template <int HT_, int NP_>
 struct PairTr {
-  static constexpr int CW = 8, PLANES = 2, AROWS = 3, APITCH = 130;
+  static constexpr int HT = HT_;
+  static constexpr int CW = 8, PLANES = 2, AROWS = HT + 2, APITCH = 130;
   static constexpr int A_PLANE_BYTES = AROWS * APITCH * 16;           // 6240
   static constexpr int A_BYTES = PLANES * A_PLANE_BYTES;              // 12480
   static constexpr int A_BYTES_AL = (A_BYTES + 127) / 128 * 128;      // 12544
-  static constexpr int NC = 128;                                      // output channels held per CTA
-  static constexpr int NP = 256;                                      // N of the pair MMA
+  static constexpr int NP = NP_;                                      // N of the pair MMA
+  static constexpr int NC = NP / 2;                                   // output channels held per CTA
   static constexpr int B_PLANE_BYTES = NC * 16;                       // 2048
   static constexpr int B_TAP_BYTES = PLANES * B_PLANE_BYTES;          // 4096
   static constexpr int B_BYTES = 9 * B_TAP_BYTES;                     // 36864
   static constexpr int STAGE_BYTES = A_BYTES_AL + B_BYTES;            // 49408
-  static constexpr int ACC_COLS = NP;                                 // one row x 256 channels per CTA
+  static constexpr int ACC_COLS = HT * NP;                            // accumulator columns per CTA and buffer
+  static constexpr int STAGES = (214 * 1024 - 256) / STAGE_BYTES > 6 ? 6 : (214 * 1024 - 256) / STAGE_BYTES;
+  static_assert(2 * ACC_COLS <= 512 && STAGES >= 3, "pair tile does not fit");
 };
 
+template <int HT, int NP>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid_constant__ ConvParams p) {
   using T = __nv_bfloat16;
-  using Tr = PairTr;
+  using Tr = PairTr<HT, NP>;
+  constexpr int kPairStages = Tr::STAGES;
   constexpr int CW = Tr::CW;
   constexpr int NT = Tr::NP;
   extern __shared__ uint8_t smem_raw[];
@@ -697,7 +706,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
   cluster_sync_all();          // the peer's barriers are initialised before anybody arrives on them remotely
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && p.trace_cap >= 8) {
+  if (p.trace != nullptr && blockIdx.x == p.trace_block && threadIdx.x == 0 && p.trace_cap >= 8) {
     p.trace[p.trace_cap - 4] = static_cast<unsigned long long>(clock64());
     p.trace[p.trace_cap - 3] = gtime();
   }
@@ -706,7 +715,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
   auto decode = [&](int t, int& b, int& y, int& xt, int& nt) {
     nt = t % p.ntiles; t /= p.ntiles;
     xt = t % p.xtiles; t /= p.xtiles;
-    y = 2 * (t % p.ytiles) + static_cast<int>(rank);     // ytiles = H / 2 row pairs; this CTA's row
+    y = HT * (2 * (t % p.ytiles) + static_cast<int>(rank));   // ytiles = H / (2 HT); first row of this CTA's tile
     b = t / p.ytiles;
   };
 
@@ -757,11 +766,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const int dy = tap / 3, dx = tap % 3;
-              const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) |
-                                     (a_lo0 + static_cast<uint32_t>(((dy * Tr::APITCH + dx) * 16) >> 4));
               const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) |
                                      (b_lo0 + static_cast<uint32_t>((tap * Tr::B_TAP_BYTES) >> 4));
-              umma_f16_pair_warp(dbase, adesc, bdesc, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
+#pragma unroll
+              for (int r = 0; r < HT; ++r) {
+                const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) |
+                                       (a_lo0 + static_cast<uint32_t>((((r + dy) * Tr::APITCH + dx) * 16) >> 4));
+                umma_f16_pair_warp(dbase + r * NT, adesc, bdesc, idesc, (ks > 0 || tap > 0) ? 1u : 0u);
+              }
             }
           }
           umma_commit_pair_warp(&empty_bar[st]);     // frees this stage in BOTH CTAs
@@ -895,7 +907,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
             return Elem<T>::pack_mma(v);
           };
           if (c0 < Ctot && p.xf.debug == 0) {
-            constexpr int XB = 3;      // 390 units per plane / 64 threads = 6.1: two batches of three
+            constexpr int XB = HT == 1 ? 3 : 4;   // 390 (520) units per plane / 64 threads: full batches, then a remainder
             int i0 = tip;
             for (; i0 + (XB - 1) * TPP < n_units; i0 += XB * TPP) {
               uint4 raw[XB];
@@ -919,13 +931,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
     // ------------------------------------------------------------------ epilogue (both CTAs, own row)
     const int ew = warp - kEpiWarp0;
     const int q = ew & 3;
-    const int half = ew >> 2;                 // which 128 of the 256 accumulator columns
+    const int half = ew >> 2;                 // HT == 1: which half of the columns; HT == 2: which row
     const int m = q * 32 + lane;
     const int Wp = p.W + 2;
     const int planes_out = p.cout_pad / CW;
     const size_t plane_stride = static_cast<size_t>(p.H) * Wp;
-    constexpr int CB = 32, NCHUNK = (NT / 2) / CB, NSUB = CB / 8;
-    const int c_begin = half * (NT / 2);
+    constexpr int CB = 32, NCHUNK = (HT == 1 ? NT / 2 : NT) / CB, NSUB = CB / 8;
+    const int c_begin = HT == 1 ? half * (NT / 2) : 0;
+    const int r_mine = HT == 1 ? 0 : half;
     const uint4* res = static_cast<const uint4*>(p.residual);
     uint4* out = static_cast<uint4*>(p.out);
     const int ethread = threadIdx.x - kEpiWarp0 * 32;
@@ -952,7 +965,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
         float ssum[NSUB][2];
 #pragma unroll
         for (int u = 0; u < NSUB; ++u) { ssum[u][0] = 0.f; ssum[u][1] = 0.f; }
-        const size_t idx0 = pt_index(b, planes_out, (n0 + c0) / CW, p.H, Wp, y, x + 1);
+        const size_t idx0 = pt_index(b, planes_out, (n0 + c0) / CW, p.H, Wp, y + r_mine, x + 1);
         uint4 rr[CB / CW];
         if (res != nullptr) {
 #pragma unroll
@@ -960,7 +973,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
         }
         float v[CB];
 #pragma unroll
-        for (int h16 = 0; h16 < CB / 16; ++h16) tmem_ld16(tbase + c0 + h16 * 16, v + h16 * 16);
+        for (int h16 = 0; h16 < CB / 16; ++h16) tmem_ld16(tbase + r_mine * NT + c0 + h16 * 16, v + h16 * 16);
         tmem_ld_wait();
         const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
@@ -1027,10 +1040,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
           for (int sc = u * cpu; sc < (u + 1) * cpu; ++sc) {
 #pragma unroll
             for (int w = 0; w < 8; ++w)
-              if ((w >> 2) == (sc >= NT / 16 ? 1 : 0)) tot += stat_w[par][w][sc][kk];
+              if (HT > 1 || (w >> 2) == (sc >= NT / 16 ? 1 : 0)) tot += stat_w[par][w][sc][kk];
           }
           const int unit = n0 / p.unit_ch + u;
-          const int slot = y * p.xtiles + xt;
+          const int slot = (y / HT) * p.xtiles + xt;
           p.stats[((static_cast<size_t>(b) * kNU + unit) * p.slots + slot) * 2 + kk] = tot;
         }
       }
@@ -1039,7 +1052,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_pair_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // nobody leaves (or frees TMEM) while the peer may still read / signal here
-  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && p.trace_cap >= 8) {
+  if (p.trace != nullptr && blockIdx.x == p.trace_block && threadIdx.x == 0 && p.trace_cap >= 8) {
     p.trace[p.trace_cap - 2] = static_cast<unsigned long long>(clock64());
     p.trace[p.trace_cap - 1] = gtime();
   }
@@ -1182,6 +1195,7 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.stages = stages;
   const int smem = 256 + (p.wres ? static_cast<int>(wbytes) : 0) + stages * p.stage_bytes;
   p.trace = g_trace; p.trace_cap = g_trace_cap;
+  { const char* e = getenv("R2DM_TRACE_BLOCK"); p.trace_block = e ? static_cast<unsigned>(atoi(e)) : 0u; }
   {
     static int cdbg = -1;
     if (cdbg < 0) { const char* e = getenv("R2DM_CONV_DEBUG"); cdbg = e ? atoi(e) : 0; }
@@ -1201,11 +1215,13 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
 }
 
 
+template <int HT, int NP>
 static cudaError_t launch_pair(const ConvLaunch& l, cudaStream_t s) {
-  using Tr = PairTr;
-  if (l.dtype != kBF16 || l.taps != 9 || l.ht != 1 || l.out_nchw != nullptr || l.out.H % 2 != 0 || l.cout_pad % 256 != 0)
+  using Tr = PairTr<HT, NP>;
+  constexpr int kPairStages = Tr::STAGES;
+  if (l.dtype != kBF16 || l.taps != 9 || l.ht != HT || l.out_nchw != nullptr || l.out.H % (2 * HT) != 0 || l.cout_pad % NP != 0)
     return cudaErrorInvalidConfiguration;
-  auto kern = conv_pair_kernel;
+  auto kern = conv_pair_kernel<HT, NP>;
   const int smem = 256 + kPairStages * Tr::STAGE_BYTES;
   static bool configured = false;
   if (!configured) {
@@ -1223,12 +1239,12 @@ static cudaError_t launch_pair(const ConvLaunch& l, cudaStream_t s) {
   p.cout = l.cout; p.cout_pad = l.cout_pad;
   p.nk = l.cin_pad / 16;
   p.ksplit = l.in1.ptr ? l.in0.C / 16 : p.nk;
-  p.xtiles = l.out.W / 128; p.ytiles = l.out.H / 2; p.ntiles = l.cout_pad / 256;
-  p.tiles_total = p.B * p.ytiles * p.xtiles * p.ntiles;      // tiles of the PAIR (2 rows x 128 px x 256 ch)
+  p.xtiles = l.out.W / 128; p.ytiles = l.out.H / (2 * HT); p.ntiles = l.cout_pad / NP;
+  p.tiles_total = p.B * p.ytiles * p.xtiles * p.ntiles;      // tiles of the PAIR (2 HT rows x 128 px x NP channels)
   p.unit_ch = l.cout / kNU >= 8 ? l.cout / kNU : 8;
   p.unit_shift = 0;
   while ((1 << p.unit_shift) < p.unit_ch) ++p.unit_shift;
-  if (p.stats != nullptr && ((1 << p.unit_shift) != p.unit_ch || p.unit_ch > 256)) return cudaErrorInvalidValue;
+  if (p.stats != nullptr && ((1 << p.unit_shift) != p.unit_ch || p.unit_ch > NP)) return cudaErrorInvalidValue;
   p.slots = l.out.slots;
   p.scale = l.scale;
   if (l.xf.enabled) {
@@ -1247,6 +1263,7 @@ static cudaError_t launch_pair(const ConvLaunch& l, cudaStream_t s) {
   }
   p.stages = kPairStages; p.stage_bytes = Tr::STAGE_BYTES;
   p.trace = g_trace; p.trace_cap = g_trace_cap;
+  { const char* e = getenv("R2DM_TRACE_BLOCK"); p.trace_block = e ? static_cast<unsigned>(atoi(e)) : 0u; }
   {
     static int cdbg = -1;
     if (cdbg < 0) { const char* e = getenv("R2DM_CONV_DEBUG"); cdbg = e ? atoi(e) : 0; }
@@ -1289,7 +1306,8 @@ static cudaError_t dispatch(const ConvLaunch& l, cudaStream_t s) {
 cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s) {
   if (l.out.W % 128 != 0 || l.cout_pad % l.nt != 0 || l.cin_pad % conv_stage_channels(l.dtype, l.taps) != 0)
     return cudaErrorInvalidValue;
-  if (l.nt == 256) return launch_pair(l, s);
+  if (l.nt == 256) return launch_pair<1, 256>(l, s);
+  if (l.pair) return l.nt == 128 ? launch_pair<2, 128>(l, s) : cudaErrorInvalidConfiguration;
   return l.dtype == kBF16 ? dispatch<__nv_bfloat16>(l, s) : dispatch<float>(l, s);
 }
 
@@ -1307,13 +1325,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     size_t r = i;
     const int cw = r % CW; r /= CW;
-    int co = r % (fuse_dy == 2 ? 128 : nt); r /= (fuse_dy == 2 ? 128 : nt);
+    int co = r % (fuse_dy == 2 ? nt / 2 : nt); r /= (fuse_dy == 2 ? nt / 2 : nt);
     int pl, tap;
     if (fuse_dy == 2) {
-      // CTA-pair layout: [rank][tap][plane][128 co][cw] per stage (conv_pair_kernel)
+      // CTA-pair layout: [rank][tap][plane][nt/2 co][cw] per stage (conv_pair_kernel)
       pl = r % planes; r /= planes;
       tap = r % taps; r /= taps;
-      co += 128 * static_cast<int>(r % 2); r /= 2;
+      co += (nt / 2) * static_cast<int>(r % 2); r /= 2;
     } else if (fuse_dy) {
       const int kyd = r % 3; r /= 3;
       pl = r % planes; r /= planes;
@@ -1339,9 +1357,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 }
 
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin, int cin_pad,
-                             int cout_pad, void* dst, cudaStream_t s) {
+                             int cout_pad, void* dst, cudaStream_t s, int pair) {
   const int planes = 2 * ks_for(taps);
-  const int fuse = (taps == 9 && nt == 256) ? 2 : (taps == 9 && (nt == 64 || nt == 128)) ? 1 : 0;
+  const int fuse = (taps == 9 && (nt == 256 || pair)) ? 2 : (taps == 9 && (nt == 64 || nt == 128)) ? 1 : 0;
   const size_t total = static_cast<size_t>(taps) * cin_pad * cout_pad;
   const int grid = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   if (dtype == kBF16)

@@ -40,6 +40,7 @@ struct ConvLaunch {
   int dtype;          // kF32 (tf32 tensor cores) or kBF16
   int taps;           // 9 (3x3 ring conv) or 1 (1x1 conv / linear over tokens)
   int nt, ht;         // N tile (output channels per CTA) and output rows per tile
+  int pair;           // nt == 128 only: CTA-pair kernel (two rows per CTA, M = 256 over two CTAs); nt == 256 implies it
   PT in0, in1;        // input(s); in1.ptr == nullptr unless the input is a channel concat
   int cin_pad;        // total input channels incl. zero padding (multiple of the stage K)
   const void* wpacked;  // packed weights (pack_conv_weight)
@@ -62,7 +63,7 @@ cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s);
 void conv_set_trace(unsigned long long* buf, int cap);
 // w: fp32 [cout][cin][k][k] (OIHW), k*k == taps
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin,
-                             int cin_pad, int cout_pad, void* dst, cudaStream_t s);
+                             int cin_pad, int cout_pad, void* dst, cudaStream_t s, int pair = 0);
 
 // ------------------------------------------------------------------ layout conversion
 cudaError_t pack_nchw(int dtype, const float* src, int B, int Csrc, int H, int W, PT dst,

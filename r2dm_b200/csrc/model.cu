@@ -35,6 +35,7 @@ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 struct ConvW {
   std::string name;
   int taps = 9, cin = 0, cout = 0, cin_pad = 0, cout_pad = 0, nt = 64;
+  int pair = 0;   // nt == 128 on the CTA-pair kernel (option pair = 2)
   size_t w_off = 0, b_off = 0;
   bool w_ok = false, b_ok = false;
 };
@@ -106,12 +107,18 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
   return static_cast<int>(m->raws.size()) - 1;
 }
 
-// CTA-pair kernel for >= 256 output channels: off by default (measured 12 % slower than the single-CTA
-// kernel in round 1); R2DM_PAIR=1 or r2dm_set_option("pair", 1) selects it
+// CTA-pair kernels (R2DM_PAIR / r2dm_set_option("pair", v)): 0 = off, 1 = 256-channel pairs (one row per
+// CTA) for layers with a multiple of 256 output channels, 2 = 128-channel pairs (two rows per CTA, six-slot
+// ring) for every 3x3 layer with a multiple of 128 output channels.  See DESIGN.md for the measurements.
 static int g_pair = -1;
-static bool pair_enabled() {
+static int pair_mode() {
   if (g_pair < 0) { const char* e = getenv("R2DM_PAIR"); g_pair = e ? atoi(e) : 0; }
-  return g_pair != 0;
+  return g_pair;
+}
+static bool pair_enabled() { return pair_mode() == 1; }
+// 128-channel pairs need tiles of 4 rows per pair
+static bool pair128(int taps, int cout, int dtype, bool rows_mult4) {
+  return pair_mode() == 2 && taps == 9 && dtype == kBF16 && cout % 128 == 0 && rows_mult4;
 }
 
 // N tile: 256 selects the CTA-pair kernel (bf16 3x3 convolutions with a multiple of 256 output channels
@@ -127,6 +134,7 @@ int add_conv(r2dm_model* m, const std::string& name, int taps, int cin, int cout
   c.name = name;
   c.taps = taps; c.cin = cin; c.cout = cout;
   c.nt = pick_nt(taps, cout, m->dtype, m->cfg.height % 16 == 0);   // every level then has an even height
+  c.pair = pair128(taps, cout, m->dtype, m->cfg.height % 32 == 0) ? 1 : 0;   // ... a multiple of 4
   c.cin_pad = round_up(cin, conv_stage_channels(m->dtype, taps));
   c.cout_pad = round_up(cout, c.nt);
   c.w_off = m->arena_bytes;
@@ -260,13 +268,13 @@ struct Builder {
     op.is_output = is_output;
     ConvLaunch& l = op.conv;
     memset(&l, 0, sizeof(l));
-    l.dtype = m->dtype; l.taps = w.taps; l.nt = w.nt;
+    l.dtype = m->dtype; l.taps = w.taps; l.nt = w.nt; l.pair = w.pair;
     if (w.taps == 9) l.ht = (w.nt == 256) ? 1 : (w.nt == 128) ? (a.H >= 2 ? 2 : 1) : (a.H % 4 == 0 ? 4 : (a.H >= 2 ? 2 : 1));
     else l.ht = a.H >= 2 ? 2 : 1;
     if (w.nt == 16 && l.ht != 4) l.ht = 4;
     // low-resolution levels: with two-row tiles fewer than half of the 148 SMs would get a tile, so
     // halve the tile (the persistent grid then covers twice as many SMs with half the K loop each)
-    if (w.taps == 9 && w.nt == 128 && l.ht == 2) {
+    if (w.taps == 9 && w.nt == 128 && l.ht == 2 && !w.pair) {
       // (decided per image, never from the batch size: the accumulation order depends on the tile
       //  shape and results must not depend on the batch composition)
       const int tiles_per_image = (a.H / 2) * (a.W / 128) * (w.cout_pad / 128);
@@ -506,7 +514,7 @@ int r2dm_load_tensor(r2dm_handle h, const char* name_c, const float* src, const 
       if (n != static_cast<size_t>(c.cout) * c.cin * c.taps)
         return fail(-3, "%s: expected %d x %d x %d elements, got %zu", name_c, c.cout, c.cin, c.taps, n);
       CUDA_TRY(pack_conv_weight(h->dtype, c.taps, c.nt, src, c.cout, c.cin, c.cin_pad, c.cout_pad,
-                                h->arena + c.w_off, s));
+                                h->arena + c.w_off, s, c.pair));
       c.w_ok = true;
     } else {
       if (n != static_cast<size_t>(c.cout)) return fail(-3, "%s: expected %d elements, got %zu", name_c, c.cout, n);
@@ -822,6 +830,7 @@ int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const floa
   memset(&l, 0, sizeof(l));
   l.dtype = dtype; l.taps = taps;
   l.nt = pick_nt(taps, Cout, dtype, H % 2 == 0);
+  l.pair = (l.nt == 128 && pair128(taps, Cout, dtype, H % 4 == 0)) ? 1 : 0;
   l.cin_pad = round_up(Cin, conv_stage_channels(dtype, taps));
   l.cout = Cout; l.cout_pad = round_up(Cout, l.nt);
   if (taps == 9) l.ht = (l.nt == 256) ? 1 : (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
@@ -835,7 +844,7 @@ int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const floa
   if (!l.in0.ptr || !l.out.ptr || !res.ptr || !wp || !bp) return fail(-1, "scratch too small");
   CUDA_TRY(cudaMemsetAsync(l.in0.ptr, 0, l.in0.bytes(dtype), s));
   CUDA_TRY(pack_nchw(dtype, x, B, Cin, H, W, l.in0, 0, s));
-  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s));
+  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s, l.pair));
   CUDA_TRY(cudaMemsetAsync(bp, 0, static_cast<size_t>(l.cout_pad) * 4, s));
   if (bias) CUDA_TRY(cudaMemcpyAsync(bp, bias, static_cast<size_t>(Cout) * 4, cudaMemcpyDeviceToDevice, s));
   if (residual) {
@@ -864,6 +873,7 @@ int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, con
   memset(&l, 0, sizeof(l));
   l.dtype = dtype; l.taps = taps;
   l.nt = pick_nt(taps, Cout, dtype, H % 2 == 0);
+  l.pair = (l.nt == 128 && pair128(taps, Cout, dtype, H % 4 == 0)) ? 1 : 0;
   l.cin_pad = round_up(Cin, conv_stage_channels(dtype, taps));
   if (l.cin_pad != Cin) return fail(-1, "Cin must be a multiple of the stage K (%d)", conv_stage_channels(dtype, taps));
   l.cout = Cout; l.cout_pad = round_up(Cout, l.nt);
@@ -878,7 +888,7 @@ int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, con
   // NOTE: the input is stored unrounded here (it is a residual-stream tensor in the network)
   CUDA_TRY(pack_nchw(dtype, x, B, Cin, H, W, l.in0, 0, s));
   CUDA_TRY(tensor_stats_launch(dtype, l.in0, s));
-  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s));
+  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s, l.pair));
   CUDA_TRY(cudaMemsetAsync(bp, 0, static_cast<size_t>(l.cout_pad) * 4, s));
   if (bias) CUDA_TRY(cudaMemcpyAsync(bp, bias, static_cast<size_t>(Cout) * 4, cudaMemcpyDeviceToDevice, s));
   l.wpacked = wp; l.bias = bp; l.scale = 1.f;
@@ -954,7 +964,7 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
 }
 
 int r2dm_set_option(const char* name, int value) {
-  if (name && std::string(name) == "pair") { g_pair = value ? 1 : 0; return 0; }
+  if (name && std::string(name) == "pair") { g_pair = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }
   return fail(-1, "unknown option %s", name ? name : "(null)");
 }
 

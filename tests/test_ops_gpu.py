@@ -158,24 +158,25 @@ def test_fused_groupnorm_conv(case, dtype):
 
 
 # ------------------------------------------------------------------------------------------ CTA pairs
-@pytest.fixture
-def pair_kernel():
-    """Select the thread-block-cluster kernel (two CTAs, tcgen05.mma.cta_group::2) for 3x3 convolutions
-    with a multiple of 256 output channels; off by default."""
+@pytest.fixture(params=[1, 2], ids=["pair256", "pair128"])
+def pair_kernel(request):
+    """Select the thread-block-cluster kernels (two CTAs, tcgen05.mma.cta_group::2): mode 1 = one row x 256
+    channels per CTA for layers with a multiple of 256 output channels, mode 2 = two rows x 128 channels per
+    CTA (six-slot ring) for a multiple of 128; off by default."""
     from r2dm_b200 import _lib
-    _lib.check(_lib.lib().r2dm_set_option(b"pair", 1), "set_option")
+    _lib.check(_lib.lib().r2dm_set_option(b"pair", request.param), "set_option")
     yield
     _lib.check(_lib.lib().r2dm_set_option(b"pair", 0), "set_option")
 
 
-@pytest.mark.parametrize("case", [(2, 128, 256, 4, 256, 3, True), (1, 64, 512, 2, 128, 3, False),
-                                  (3, 256, 256, 8, 128, 3, True)])
+@pytest.mark.parametrize("case", [(2, 128, 256, 4, 256, 3, True), (1, 64, 512, 4, 128, 3, False),
+                                  (3, 256, 256, 8, 128, 3, True), (2, 64, 128, 8, 256, 3, False)])
 def test_conv_cta_pair(pair_kernel, case):
     test_conv(case, "bf16")
 
 
-@pytest.mark.parametrize("case", [(2, 256, 256, 4, 128, 3, True), (1, 128, 512, 6, 256, 3, False),
-                                  (2, 512, 512, 2, 128, 3, True)])
+@pytest.mark.parametrize("case", [(2, 256, 256, 4, 128, 3, True), (1, 128, 512, 8, 256, 3, False),
+                                  (2, 512, 512, 4, 128, 3, True), (2, 128, 128, 8, 256, 3, True)])
 def test_fused_groupnorm_conv_cta_pair(pair_kernel, case):
     test_fused_groupnorm_conv(case, "bf16")
 

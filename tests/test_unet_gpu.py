@@ -40,10 +40,12 @@ def test_forward_matches_reference_golden(golden, tag, precision):
     assert e <= TOL[precision], f"{tag}/{precision}: l2-rel {e:.3e}"
 
 
-def test_forward_with_cta_pair_kernel(golden):
-    """Config H with the 256/512-channel 3x3 convolutions on the CTA-pair kernel (opt-in)."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_forward_with_cta_pair_kernel(golden, mode):
+    """Config H with the eligible 3x3 convolutions on the CTA-pair kernels (opt-in; mode 1 = 256-channel
+    pairs, mode 2 = 128-channel pairs)."""
     from r2dm_b200 import _lib
-    _lib.check(_lib.lib().r2dm_set_option(b"pair", 1), "set_option")
+    _lib.check(_lib.lib().r2dm_set_option(b"pair", mode), "set_option")
     try:
         gd = golden["H"]
         sd = O.random_state_dict(H_CFG, gd["seed_weights"])

@@ -1,6 +1,2 @@
-for shape in "256 256 16 256 1" "512 512 8 128 1" "128 256 32 512 0" "256 256 8 128 1"; do
-  for v in 0 1; do
-    echo "== shape $shape PAIR=$v"
-    R2DM_PAIR=$v ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"conv_umma|conv_pair" -s 2 -c 3 python tools/ncu_conv.py $shape 5 2>&1 | grep -E "gpu__time_duration" | awk '{print $NF, $(NF-1)}' | tr '\n' ' '; echo
-  done
-done
+R2DM_PAIR=2 timeout 200 python -m pytest tests/test_ops_gpu.py tests/test_unet_gpu.py -x -q -k "test_conv or test_fused_groupnorm_conv or forward_matches" 2>&1 | tail -4
+R2DM_PAIR=2 R2DM_PRINT_PROFILE=1 timeout 200 python tools/profile_forward.py 3 > gpurun_out/s26_profile.txt 2>&1; head -3 gpurun_out/s26_profile.txt
