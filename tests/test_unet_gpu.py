@@ -60,6 +60,24 @@ def test_forward_with_cta_pair_kernel(golden, mode):
     assert e <= TOL["bf16"], f"H/bf16/pair: l2-rel {e:.3e}"
 
 
+@pytest.mark.parametrize("enc", ["spherical_harmonics", "polar_coordinates", None])
+def test_forward_other_coordinate_encodings(enc):
+    """efficient_unet.py:221-229: the spherical-harmonics (25 ch), polar (2 ch) and no encoding variants of
+    the input stage against the CPU oracle (the goldens cover Fourier features only)."""
+    import dataclasses
+    cfg = dataclasses.replace(SMALL_CFG, coords_encoding=enc)
+    sd = O.random_state_dict(cfg, 21)
+    ddpm = make_ddpm(cfg, sd, precision="fp32")
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, cfg.in_channels, *cfg.resolution, generator=g)
+    cond = torch.tensor([1.5])
+    y = ddpm.model(x.cuda(), cond.cuda())
+    torch.cuda.synchronize()
+    ref = O.unet_forward(sd, cfg, x, cond)
+    e = rel_l2(y, ref)
+    assert e <= TOL["fp32"], f"{enc}: l2-rel {e:.3e}"
+
+
 def test_batch_composition_invariance():
     """Sample i's prediction must not depend on its batch neighbours."""
     cfg = SMALL_CFG
