@@ -490,10 +490,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       decode(t, b, yt, xt, nt);
       const int n0 = nt * NT, x = xt * 128 + m, y0 = yt * HT;
       const int buf = j & 1, par = j & 1;
+      const bool edge_warp = (xt == 0 && q == 0) || (xt == p.xtiles - 1 && q == 3);   // holds pixel 0 or W-1
       if (nt != cur_nt) {   // bias of this N tile -> shared memory (once per CTA when ntiles == 1)
         cur_nt = nt;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = ethread; i < NT; i += 256) bias_s[i] = p.bias[n0 + i];
+        for (int i = ethread; i < NT; i += 256) bias_s[i] = p.bias[n0 + i] * p.scale;   // pre-scaled: one FMA per value
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       if (!NCHW && res != nullptr) {
@@ -535,15 +536,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
             for (int i4 = 0; i4 < CB / 4; ++i4) {
-              const float4 bv = bias4[i4];
-              v[4 * i4] += bv.x; v[4 * i4 + 1] += bv.y; v[4 * i4 + 2] += bv.z; v[4 * i4 + 3] += bv.w;
+              const float4 bv = bias4[i4];      // (acc + bias) * scale = acc * scale + bias * scale
+              v[4 * i4] = fmaf(v[4 * i4], p.scale, bv.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], p.scale, bv.y);
+              v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], p.scale, bv.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], p.scale, bv.w);
             }
             if constexpr (NCHW) {
               float* dst = p.out_nchw + ((static_cast<size_t>(b) * p.cout + n0 + c0) * p.H + y) * p.W + x;
               const size_t cstride = static_cast<size_t>(p.H) * p.W;
 #pragma unroll
               for (int i = 0; i < CB; ++i)
-                if (n0 + c0 + i < p.cout) dst[i * cstride] = v[i] * p.scale;
+                if (n0 + c0 + i < p.cout) dst[i * cstride] = v[i];
             } else {
 #pragma unroll
               for (int u = 0; u < CB / CW; ++u) {
@@ -555,17 +557,19 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                   float rv[CW];
                   Elem<T>::unpack(rr[u], rv);
 #pragma unroll
-                  for (int i = 0; i < CW; ++i) o[i] += rv[i];
+                  for (int i = 0; i < CW; ++i) o[i] = fmaf(rv[i], p.scale, o[i]);
                 }
                 float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int i = 0; i < CW; ++i) { o[i] *= p.scale; s1 += o[i]; s2 = fmaf(o[i], o[i], s2); }
+                for (int i = 0; i < CW; ++i) { s1 += o[i]; s2 = fmaf(o[i], o[i], s2); }
                 ssum[(u * CW) / 8][0] += s1;
                 ssum[(u * CW) / 8][1] += s2;
                 const uint4 pk = Elem<T>::pack(o);
                 out[idx] = pk;
-                if (x == 0) out[idx + p.W] = pk;              // xp = W+1 mirrors pixel 0
-                if (x == p.W - 1) out[idx - p.W] = pk;        // xp = 0 mirrors pixel W-1
+                if (edge_warp) {                              // warp-uniform: only the two warps at the seam
+                  if (x == 0) out[idx + p.W] = pk;            // xp = W+1 mirrors pixel 0
+                  if (x == p.W - 1) out[idx - p.W] = pk;      // xp = 0 mirrors pixel W-1
+                }
               }
             }
           }
