@@ -315,6 +315,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     // so two stages are in flight and the XU (tanh) pipe of every SM sub-partition always has a
     // second warp to issue from while the first waits on shared memory.
     if (p.xf.enabled) {
+      const double inv_cnt = 1.0 / (static_cast<double>((p.xf.C0 + p.xf.C1) / p.xf.groups) * p.H * p.W);
       pdl_wait();
       const int grp = (warp - 4) >> 2;                  // 0 / 1
       const int t256 = threadIdx.x - 128;               // 0..255 over both groups
@@ -329,7 +330,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       for (int t = t_begin; t < t_end; ++t) {
         int b, yt, xt, nt;
         decode(t, b, yt, xt, nt);
-        if (b != cur_b) {
+        if (b != cur_b && !(p.xf.debug & 4)) {   // (debug 4: developer ablation, no statistics fold)
           // ---- fold statistics + affine/FiLM into per-channel (a, d) for image b (all 8 warps; the
           // first barrier also guarantees that nobody still reads the previous image's table)
           cur_b = b;
@@ -352,9 +353,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               be_r[k] = fl ? fl[Ctot + c] : p.xf.beta[c];
             }
           }
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          if (grp == 0) {
-            const int g = tt >> 4, l16 = tt & 15;        // 16 threads per group (groups == 8)
+          {
+            // one warp per GroupNorm group (groups == 8): every lane issues all its loads before the first add
+            const int g = t256 >> 5;
             double s1 = 0.0, s2 = 0.0;
             const int lo = g * gsize, hi_c = lo + gsize;
             int off = 0;
@@ -369,27 +370,26 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 const int u0 = (a - off) / unit_ch, u1 = (e - off) / unit_ch;
                 const int n = (u1 - u0) * sl;
                 const float2* st2 = reinterpret_cast<const float2*>(stp + (static_cast<size_t>(b) * kNU + u0) * sl * 2);
-                // four independent loads in flight per thread, fp32 partial sums of at most four
-                // tile sums each, folded in double
-                int i = l16;
-                for (; i + 48 < n; i += 64) {
-                  const float2 v0 = st2[i], v1 = st2[i + 16], v2 = st2[i + 32], v3 = st2[i + 48];
-                  s1 += (static_cast<double>(v0.x) + v1.x) + (static_cast<double>(v2.x) + v3.x);
-                  s2 += (static_cast<double>(v0.y) + v1.y) + (static_cast<double>(v2.y) + v3.y);
+                for (int i = lane; i < n; i += 128) {
+                  float2 v[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) v[u] = i + 32 * u < n ? st2[i + 32 * u] : make_float2(0.f, 0.f);
+                  s1 += (static_cast<double>(v[0].x) + v[1].x) + (static_cast<double>(v[2].x) + v[3].x);
+                  s2 += (static_cast<double>(v[0].y) + v[1].y) + (static_cast<double>(v[2].y) + v[3].y);
                 }
-                for (; i < n; i += 16) { const float2 v = st2[i]; s1 += v.x; s2 += v.y; }
               }
               off += Cs;
             }
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
+            for (int o = 16; o > 0; o >>= 1) {
               s1 += __shfl_xor_sync(0xffffffffu, s1, o);
               s2 += __shfl_xor_sync(0xffffffffu, s2, o);
             }
-            if (l16 == 0) {
-              const double cnt = static_cast<double>(gsize) * p.H * p.W;
-              const double mean = s1 / cnt;
-              double var = s2 / cnt - mean * mean;
+            // the previous image's table may still be in use until everybody is here
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (lane == 0) {
+              const double mean = s1 * inv_cnt;
+              double var = s2 * inv_cnt - mean * mean;
               if (var < 0.0) var = 0.0;
               grp_s[0][g] = static_cast<float>(mean);
               grp_s[1][g] = rsqrtf(static_cast<float>(var) + p.xf.eps);
