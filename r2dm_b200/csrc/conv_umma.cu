@@ -86,13 +86,13 @@ struct ConvTraits {
   static constexpr int A_PLANE_BYTES = AROWS * APITCH * 16;
   static constexpr int A_BYTES = PLANES * A_PLANE_BYTES;
   static constexpr int A_BYTES_AL = (A_BYTES + 127) / 128 * 128;
-  // FUSE (3x3, NT = 64; NT = 128 fuses two taps, N = 256): the vertical taps of one horizontal offset
+  // FUSE (3x3, NT = 64 and NT = 16 (N = 48); NT = 128 fuses two taps, N = 256): the vertical taps of one horizontal offset
   // are ONE MMA with N = 192:
   // the shifted A view of input row i feeds output rows i-1, i, i+1 (adjacent accumulator column
   // blocks), because a 128x64x16 MMA cannot go below ~60 cycles (53 % of the tensor pipe, measured
   // with tools/probe_mma_rate.cu) while N >= 128 runs at full rate.  Weights are then packed as
   // [kx][plane][ky descending][co] so that any contiguous ky range is a contiguous row range of B.
-  static constexpr bool FUSE = (TAPS == 9 && (NT == 64 || (NT == 128 && HT <= 2)));
+  static constexpr bool FUSE = (TAPS == 9 && (NT == 64 || NT == 16 || (NT == 128 && HT <= 2)));
   static constexpr int B_PLANE_BYTES = (FUSE ? 3 : 1) * NT * 16;
   static constexpr int B_TAP_BYTES = PLANES * B_PLANE_BYTES;          // one tap (or one kx block)
   static constexpr int B_BYTES = (FUSE ? 3 : TAPS) * B_TAP_BYTES;
@@ -1363,7 +1363,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin, int cin_pad,
                              int cout_pad, void* dst, cudaStream_t s, int pair) {
   const int planes = 2 * ks_for(taps);
-  const int fuse = (taps == 9 && (nt == 256 || pair)) ? 2 : (taps == 9 && (nt == 64 || nt == 128)) ? 1 : 0;
+  const int fuse = (taps == 9 && (nt == 256 || pair)) ? 2 : (taps == 9 && (nt == 64 || nt == 128 || nt == 16)) ? 1 : 0;
   const size_t total = static_cast<size_t>(taps) * cin_pad * cout_pad;
   const int grid = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   if (dtype == kBF16)
