@@ -1139,7 +1139,18 @@ static int num_sms() {
 
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cap = 0;
-void conv_set_trace(unsigned long long* buf, int cap) { g_trace = buf; g_trace_cap = cap; }
+static int g_trace_skip = 0;      // developer: trace only the (skip+1)-th conv launch after conv_set_trace
+void conv_set_trace(unsigned long long* buf, int cap) {
+  g_trace = buf; g_trace_cap = cap;
+  const char* e = getenv("R2DM_TRACE_SKIP");
+  g_trace_skip = (buf && e) ? atoi(e) : 0;
+}
+// the trace buffer for this launch (null unless it is the selected one)
+static unsigned long long* trace_for_this_launch() {
+  if (g_trace == nullptr) return nullptr;
+  if (getenv("R2DM_TRACE_SKIP") == nullptr) return g_trace;     // legacy: every launch writes (last one wins)
+  return g_trace_skip-- == 0 ? g_trace : nullptr;
+}
 
 constexpr int kSmemBudget = 216 * 1024;     // dynamic smem per CTA (227 KB limit minus ~9.5 KB static)
 constexpr int kWresMaxBytes = 80 * 1024;    // keep the filter bank resident below this size
@@ -1198,7 +1209,7 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   if (stages < 2) return cudaErrorInvalidConfiguration;
   p.stages = stages;
   const int smem = 256 + (p.wres ? static_cast<int>(wbytes) : 0) + stages * p.stage_bytes;
-  p.trace = g_trace; p.trace_cap = g_trace_cap;
+  p.trace = trace_for_this_launch(); p.trace_cap = g_trace_cap;
   { const char* e = getenv("R2DM_TRACE_BLOCK"); p.trace_block = e ? static_cast<unsigned>(atoi(e)) : 0u; }
   {
     static int cdbg = -1;
@@ -1266,7 +1277,7 @@ static cudaError_t launch_pair(const ConvLaunch& l, cudaStream_t s) {
     if (x.C0 + x.C1 > kMaxCin || x.stats0 == nullptr) return cudaErrorInvalidValue;
   }
   p.stages = kPairStages; p.stage_bytes = Tr::STAGE_BYTES;
-  p.trace = g_trace; p.trace_cap = g_trace_cap;
+  p.trace = trace_for_this_launch(); p.trace_cap = g_trace_cap;
   { const char* e = getenv("R2DM_TRACE_BLOCK"); p.trace_block = e ? static_cast<unsigned>(atoi(e)) : 0u; }
   {
     static int cdbg = -1;
