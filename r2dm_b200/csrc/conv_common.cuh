@@ -1,0 +1,78 @@
+// Shared by the single-CTA (conv_umma.cu) and CTA-pair (conv_pair.cu) convolution kernels: kernel
+// parameter block, developer trace hooks and small device helpers.
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace r2dm {
+
+constexpr int kMaxStages = 8;
+constexpr int kConvThreads = 640;   // 4 control warps + 2 x 4 transform warps + 8 epilogue warps
+constexpr int kEpiWarp0 = 12;       // first epilogue warp (multiple of 4: TMEM lane quarter = warp % 4)
+constexpr int kMaxCin = 1024;
+
+struct XformParams {
+  int enabled, silu;
+  const float* stats0; const float* stats1;   // partial (sum, sumsq) of the source tensor(s)
+  int C0, C1, slots0, slots1;
+  const float* gamma; const float* beta;      // affine GroupNorm, or
+  const float* film;                          // AdaGN table (scale at film_off, shift at +Ctot)
+  int film_stride, film_off;
+  const int* step_ptr; int rows_per_step, row_batch_stride;
+  int groups; float eps;
+  int debug;   // developer knob (R2DM_XF_DEBUG): 1 = skip transform math+copy, 2 = copy only
+};
+
+struct ConvParams {
+  CUtensorMap tmap0, tmap1;
+  XformParams xf;
+  const void* wpacked;
+  const float* bias;
+  const void* residual;
+  void* out;
+  float* out_nchw;
+  float* stats;
+  int B, H, W;
+  int cout, cout_pad;     // real / padded output channels
+  int nk, ksplit;         // pipeline stages over K; first stage that reads from tmap1
+  int xtiles, ytiles, ntiles, tiles_total;
+  int unit_ch;            // output channels per statistics unit (cout / kNU), a power of two
+  int unit_shift;         // log2(unit_ch)
+  int slots;
+  float scale;
+  int stages, stage_bytes, wres;  // smem ring depth / stride; weights resident in smem
+  int debug;  // developer ablation knob (R2DM_CONV_DEBUG): 1 no epilogue stores, 2 no MMA issue, 4 no TMA
+  unsigned long long* trace;  // developer timeline (r2dm_debug_set_trace): [5 roles][cap] clock64 of CTA 0
+  int trace_cap;
+  unsigned trace_block;   // CTA whose roles are traced (R2DM_TRACE_BLOCK, default 0)
+};
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define R2DM_TRACE(role, idx)                                                          \
+  do {                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == p.trace_block && (idx) < p.trace_cap)      \
+      p.trace[(role) * p.trace_cap + (idx)] = static_cast<unsigned long long>(clock64()); \
+  } while (0)
+
+__device__ __forceinline__ float silu_from_half(float h) {
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(h));
+  return fmaf(h, th, h);
+}
+
+// ---- host-side helpers defined in conv_umma.cu
+int conv_num_sms();
+// trace buffer for the launch being prepared (null unless tracing is on and this launch is selected)
+unsigned long long* conv_trace_for_this_launch();
+int conv_trace_cap();
+cudaError_t conv_pair_launch(const ConvLaunch& l, cudaStream_t s);   // conv_pair.cu
+
+}  // namespace r2dm
