@@ -731,6 +731,11 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
     p.debug = cdbg;
   }
   int grid = conv_num_sms();
+  {
+    static int cap = -1;   // developer knob: cap the persistent grid (R2DM_CONV_GRID), e.g. to share the GPU between streams
+    if (cap < 0) { const char* e = getenv("R2DM_CONV_GRID"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && grid > cap) grid = cap;
+  }
   if (grid > p.tiles_total) grid = p.tiles_total;
   static int pdl = -1;
   if (pdl < 0) { const char* e = getenv("R2DM_PDL"); pdl = e ? atoi(e) : 1; }
