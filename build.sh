@@ -7,10 +7,10 @@ OUT=r2dm_b200/libr2dm_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr"
 mkdir -p build/obj
 pids=()
-for f in conv_umma conv_pair elementwise attention attention_umma model; do
+for f in conv_umma elementwise attention attention_umma model; do
   nvcc $FLAGS ${PTXAS_V:+-Xptxas -v} -c $SRC/$f.cu -o build/obj/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -o $OUT build/obj/conv_umma.o build/obj/conv_pair.o build/obj/elementwise.o build/obj/attention.o build/obj/attention_umma.o build/obj/model.o -cudart static
+nvcc -shared -o $OUT build/obj/conv_umma.o build/obj/elementwise.o build/obj/attention.o build/obj/attention_umma.o build/obj/model.o -cudart static
 echo "built $OUT"

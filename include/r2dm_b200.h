@@ -105,6 +105,33 @@ int r2dm_axpby_table(float* y, const float* x, const float* noise, const float* 
                      int rows_per_step, int row_batch_stride, int batch, size_t per_sample, void* stream);
 int r2dm_advance_step(int* step_ptr, int delta, void* stream);
 
+/* --- noise drawn on the device (models/diffusion/base.py:71-94 with `rng` = a list of per-sample CUDA
+ * generators): the same arithmetic as above with the noise generated inside the kernel, bit-identical
+ * to `torch.randn(per_sample elements, generator=g_b)` on this device, so that a whole sampling loop
+ * replays as CUDA graphs without host-side draws in between.  Sample b's j-th draw of the loop reads
+ * the Philox4x32-10 stream (seeds[b], offsets[b] + offset_per_draw * j), j = mul0 * *ctr0 +
+ * mul1 * *ctr1 + <draw index of the call> (NULL counters read as 0); `threads` / `offset_per_draw`
+ * are ATen's launch width and per-call offset increment for a tensor of per_sample elements
+ * (r2dm_b200/diffusion.py::_torch_randn_geometry). */
+typedef struct {
+  const uint64_t* seeds;    /* device [batch] */
+  const uint64_t* offsets;  /* device [batch] */
+  const int* ctr0; const int* ctr1;
+  int mul0, mul1;
+  uint32_t offset_per_draw, threads;
+} r2dm_philox;
+/* r2dm_sampler_update with generated noise; draw_noise2 (known-region draw, RePaint) is ignored when known == NULL */
+int r2dm_sampler_update_philox(float* x_out, const float* x, const float* pred, const float* coef, int coef_cols,
+                               const int* step_ptr, int rows_per_step, int row_batch_stride, float clip,
+                               const float* known, const float* mask, const r2dm_philox* philox, int draw_noise,
+                               int draw_noise2, int batch, size_t per_sample, void* stream);
+/* r2dm_axpby_table with generated noise */
+int r2dm_axpby_table_philox(float* y, const float* x, const float* table, const int* step_ptr, int rows_per_step,
+                            int row_batch_stride, const r2dm_philox* philox, int draw, int batch,
+                            size_t per_sample, void* stream);
+/* out[b][per_sample] = that draw itself (x_T, tests) */
+int r2dm_philox_normal(float* out, const r2dm_philox* philox, int draw, int batch, size_t per_sample, void* stream);
+
 /* --- LiDAR post-processing (sample_and_save.py:52-57, utils/lidar.py:49-70,99-120):
  * sample [B][2][H][W] in [-1,1] -> out [B][5][H][W] = depth, x, y, z, reflectance.
  * depth_format: 0 log_depth, 1 inverse_depth, 2 depth.  angles: [2][H][W] (elevation, azimuth). */
@@ -138,11 +165,8 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
  * returns channel count via *C_out etc.  Names: "in_conv", "<block>", "<block>.rb<i>". */
 /* developer aid: record a per-role globaltimer timeline of CTA 0 of subsequent conv launches into
  * buf[4][cap] (uint64 ns; roles: producer, MMA, transform, epilogue); NULL disables. */
-/* Process-wide kernel-selection options, read when a model is created / an r2dm_op_* call is planned.
- *   "pair" = 1: 3x3 convolutions with a multiple of 256 output channels (bf16, even height) run on the
- *               thread-block-cluster kernel (two CTAs, tcgen05.mma.cta_group::2, one row x 256 channels per CTA);
- *          = 2: every 3x3 convolution with a multiple of 128 output channels (height a multiple of 4) runs on
- *               its two-rows x 128-channels variant; default 0 (single-CTA kernels). */
+/* Process-wide developer options, read when a model is created / an r2dm_op_* call is planned
+ * (see INTEGRATION.md "Options"); unknown names return an error. */
 int r2dm_set_option(const char* name, int value);
 int r2dm_debug_set_trace(void* buf, int cap);
 int r2dm_debug_tensor(r2dm_handle h, const char* name, float* out, int* C, int* H, int* W, void* stream);

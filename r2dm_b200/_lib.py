@@ -35,6 +35,14 @@ class R2dmConfig(C.Structure):
     ]
 
 
+class R2dmPhilox(C.Structure):
+    """r2dm_philox (include/r2dm_b200.h): device-side noise stream description."""
+    _fields_ = [
+        ("seeds", C.c_void_p), ("offsets", C.c_void_p), ("ctr0", C.c_void_p), ("ctr1", C.c_void_p),
+        ("mul0", C.c_int), ("mul1", C.c_int), ("offset_per_draw", C.c_uint32), ("threads", C.c_uint32),
+    ]
+
+
 class R2dmError(RuntimeError):
     pass
 
@@ -64,6 +72,11 @@ _SIGS = {
     "r2dm_axpby": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_size_t, _P]),
     "r2dm_axpby_table": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_size_t, _P]),
     "r2dm_advance_step": (C.c_int, [_P, C.c_int, _P]),
+    "r2dm_sampler_update_philox": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_float, _P, _P,
+                                             C.POINTER(R2dmPhilox), C.c_int, C.c_int, C.c_int, C.c_size_t, _P]),
+    "r2dm_axpby_table_philox": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(R2dmPhilox), C.c_int,
+                                          C.c_int, C.c_size_t, _P]),
+    "r2dm_philox_normal": (C.c_int, [_P, C.POINTER(R2dmPhilox), C.c_int, C.c_int, C.c_size_t, _P]),
     "r2dm_lidar_postprocess": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_float, _P]),
     "r2dm_op_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

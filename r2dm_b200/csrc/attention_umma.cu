@@ -190,11 +190,10 @@ template <int HD>
 static cudaError_t launch_attn(const PT& qkv, const PT& out, int heads, const CUtensorMap& tm, cudaStream_t s) {
   constexpr int SMEM = (5 * (HD / 8) * 128 * 16) + 16 * 128 * 16 + 256;
   auto kern = attention_umma_kernel<HD>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;   // one bit per device (the attribute is per device)
+  if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   AttnParams p;
   p.tmap = tm;

@@ -1,5 +1,4 @@
-// Shared by the single-CTA (conv_umma.cu) and CTA-pair (conv_pair.cu) convolution kernels: kernel
-// parameter block, developer trace hooks and small device helpers.
+// Convolution kernel parameter block, developer trace hooks and small device helpers.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -45,6 +44,8 @@ struct ConvParams {
   int slots;
   float scale;
   int stages, stage_bytes, wres;  // smem ring depth / stride; weights resident in smem
+  int coef_ch, coef_bytes;        // transform coefficient table at the start of dynamic smem: 2 x coef_ch floats
+  int reverse;                    // walk the tiles back to front
   int debug;  // developer ablation knob (R2DM_CONV_DEBUG): 1 no epilogue stores, 2 no MMA issue, 4 no TMA
   unsigned long long* trace;  // developer timeline (r2dm_debug_set_trace): [5 roles][cap] clock64 of CTA 0
   int trace_cap;
@@ -73,6 +74,5 @@ int conv_num_sms();
 // trace buffer for the launch being prepared (null unless tracing is on and this launch is selected)
 unsigned long long* conv_trace_for_this_launch();
 int conv_trace_cap();
-cudaError_t conv_pair_launch(const ConvLaunch& l, cudaStream_t s);   // conv_pair.cu
 
 }  // namespace r2dm

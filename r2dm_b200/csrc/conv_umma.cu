@@ -69,7 +69,6 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __shared__ uint64_t acc_full[2], acc_empty[2], wres_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float stat_w[2][8][NT / 8 > 0 ? NT / 8 : 1][2];   // [tile parity][epilogue warp][8-channel sub-chunk][sum, sumsq]
-  __shared__ float coef_s[2][kMaxCin];
   __shared__ float grp_s[2][kNU];
   __shared__ __align__(16) float bias_s[NT];
 
@@ -77,8 +76,11 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.tiles_total / gridDim.x);
   const int t_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.tiles_total / gridDim.x);
   const uint32_t wres_bytes = p.wres ? static_cast<uint32_t>(p.nk) * Tr::B_BYTES : 0u;
-  uint8_t* smem_w = smem;                 // resident weights (if any)
-  uint8_t* smem_ring = smem + wres_bytes; // stage ring
+  // dynamic shared memory: [transform coefficients a_c | d_c (2 x coef_ch floats)] [resident weights] [ring]
+  float* coef_a = reinterpret_cast<float*>(smem);
+  float* coef_d = coef_a + p.coef_ch;
+  uint8_t* smem_w = smem + p.coef_bytes;  // resident weights (if any)
+  uint8_t* smem_ring = smem_w + wres_bytes; // stage ring
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&xf_bar[i], 4); }
@@ -103,7 +105,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   // activation / statistics / output address is touched before pdl_wait().
   pdl_launch_dependents();
 
+  // p.reverse: this launch walks the tiles back to front, so that it starts with what the previous launch
+  // wrote last (still in L2) instead of with what it wrote first (evicted when a tensor exceeds L2)
   auto decode = [&](int t, int& b, int& yt, int& xt, int& nt) {
+    if (p.reverse) t = p.tiles_total - 1 - t;
     nt = t % p.ntiles; t /= p.ntiles;
     xt = t % p.xtiles; t /= p.xtiles;
     yt = t % p.ytiles;
@@ -341,8 +346,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             if (c < Ctot) {
               const int g = c / gsize;
               const float a = grp_s[1][g] * ga_r[k];
-              coef_s[0][c] = a * fold;
-              coef_s[1][c] = (be_r[k] - grp_s[0][g] * a) * fold;
+              coef_a[c] = a * fold;
+              coef_d[c] = (be_r[k] - grp_s[0][g] * a) * fold;
             }
           }
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -358,8 +363,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
           for (int i = 0; i < CW; ++i) {
             const bool ok = c0 + i < Ctot;
-            ca[i] = ok ? coef_s[0][c0 + i] : 0.f;
-            cd[i] = ok ? coef_s[1][c0 + i] : 0.f;
+            ca[i] = ok ? coef_a[c0 + i] : 0.f;
+            cd[i] = ok ? coef_d[c0 + i] : 0.f;
           }
           mbar_wait_relaxed(&full_bar[st], ph, 500);
           if (tt == 0) R2DM_TRACE(grp ? 4 : 2, 2 * it);
@@ -641,13 +646,12 @@ int conv_make_tmaps(ConvLaunch& l) {
 }
 
 int conv_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
+  static int n[64] = {0};   // per device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = n[dev & 63];
+  if (v == 0 && (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)) v = 148;
+  return v;
 }
 
 static unsigned long long* g_trace = nullptr;
@@ -666,7 +670,7 @@ unsigned long long* conv_trace_for_this_launch() {
 }
 int conv_trace_cap() { return g_trace_cap; }
 
-constexpr int kSmemBudget = 216 * 1024;     // dynamic smem per CTA (227 KB limit minus ~9.5 KB static)
+constexpr int kSmemBudget = 224 * 1024;     // dynamic smem per CTA (227 KB limit minus < 3 KB static)
 constexpr int kWresMaxBytes = 80 * 1024;    // keep the filter bank resident below this size
 
 template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW = false>
@@ -674,11 +678,10 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
   auto kern = conv_umma_kernel<T, NT, HT, TAPS, KS, NCHW>;
   if ((l.out_nchw != nullptr) != NCHW) return cudaErrorInvalidConfiguration;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;   // one bit per device (the attribute is per device)
+  if (first_use_on_this_device(configured)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   ConvParams p;
   memset(&p, 0, sizeof(p));
@@ -717,12 +720,15 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   const size_t wbytes = static_cast<size_t>(p.nk) * Tr::B_BYTES;
   p.wres = (p.ntiles == 1 && wbytes <= static_cast<size_t>(kWresMaxBytes)) ? 1 : 0;
   p.stage_bytes = Tr::A_BYTES_AL + (p.wres ? 0 : Tr::B_BYTES);
-  const int avail = kSmemBudget - 256 - (p.wres ? static_cast<int>(wbytes) : 0);
+  p.coef_ch = l.xf.enabled ? (p.xf.C0 + p.xf.C1 + 31) / 32 * 32 : 0;
+  p.coef_bytes = 2 * p.coef_ch * static_cast<int>(sizeof(float));
+  p.reverse = l.reverse;
+  const int avail = kSmemBudget - 256 - p.coef_bytes - (p.wres ? static_cast<int>(wbytes) : 0);
   int stages = avail / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return cudaErrorInvalidConfiguration;
   p.stages = stages;
-  const int smem = 256 + (p.wres ? static_cast<int>(wbytes) : 0) + stages * p.stage_bytes;
+  const int smem = 256 + p.coef_bytes + (p.wres ? static_cast<int>(wbytes) : 0) + stages * p.stage_bytes;
   p.trace = conv_trace_for_this_launch(); p.trace_cap = g_trace_cap;
   { const char* e = getenv("R2DM_TRACE_BLOCK"); p.trace_block = e ? static_cast<unsigned>(atoi(e)) : 0u; }
   {
@@ -770,7 +776,6 @@ static cudaError_t dispatch(const ConvLaunch& l, cudaStream_t s) {
 cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s) {
   if (l.out.W % 128 != 0 || l.cout_pad % l.nt != 0 || l.cin_pad % conv_stage_channels(l.dtype, l.taps) != 0)
     return cudaErrorInvalidValue;
-  if (l.nt == 256 || l.pair) return conv_pair_launch(l, s);
   return l.dtype == kBF16 ? dispatch<__nv_bfloat16>(l, s) : dispatch<float>(l, s);
 }
 
@@ -788,14 +793,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     size_t r = i;
     const int cw = r % CW; r /= CW;
-    int co = r % (fuse_dy == 2 ? nt / 2 : nt); r /= (fuse_dy == 2 ? nt / 2 : nt);
+    const int co = r % nt; r /= nt;
     int pl, tap;
-    if (fuse_dy == 2) {
-      // CTA-pair layout: [rank][tap][plane][nt/2 co][cw] per stage (conv_pair_kernel)
-      pl = r % planes; r /= planes;
-      tap = r % taps; r /= taps;
-      co += (nt / 2) * static_cast<int>(r % 2); r /= 2;
-    } else if (fuse_dy) {
+    if (fuse_dy) {
       const int kyd = r % 3; r /= 3;
       pl = r % planes; r /= planes;
       const int kx = r % 3; r /= 3;
@@ -820,9 +820,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 }
 
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin, int cin_pad,
-                             int cout_pad, void* dst, cudaStream_t s, int pair) {
+                             int cout_pad, void* dst, cudaStream_t s) {
   const int planes = 2 * ks_for(taps);
-  const int fuse = (taps == 9 && (nt == 256 || pair)) ? 2 : (taps == 9 && (nt == 64 || nt == 128 || nt == 16)) ? 1 : 0;
+  const int fuse = (taps == 9 && (nt == 64 || nt == 128 || nt == 16)) ? 1 : 0;
   const size_t total = static_cast<size_t>(taps) * cin_pad * cout_pad;
   const int grid = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   if (dtype == kBF16)

@@ -1,6 +1,8 @@
 // HBM-bound kernels of the sampling path: layout conversion, GroupNorm/AdaGN(+SiLU) apply,
 // closed-form FIR resampling, the conditioning (time-embedding / FiLM) table and the fused
 // sampler update.  All activation traffic is 16-byte vectorised along the 1024-wide azimuth axis.
+#include <cstring>
+#include <curand_kernel.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -490,6 +492,23 @@ cudaError_t cond_embed_launch(const CondEmbed& c, cudaStream_t s) {
 // continuous_time.py:208-229 / discrete_time.py:140-179 folded into per-step scalar coefficients:
 //   x0 = clamp(ux x_t + up pred) ;  x_s = kx x_t + k0 x0 + kn noise
 // and, for RePaint (continuous_time.py:296-299), x_s = mask (qa known + qs noise2) + (1-mask) x_s.
+// ---- in-kernel noise: Philox4x32-10 + Box-Muller through the cuRAND device API, laid out like ATen's
+// normal_ kernel so that the values equal torch.randn(generator=<CUDA generator>) bit for bit.
+__device__ __forceinline__ unsigned long long philox_base_offset(const PhiloxDraw& ph, int b, int index) {
+  const int draw = (ph.ctr0 ? ph.mul0 * *ph.ctr0 : 0) + (ph.ctr1 ? ph.mul1 * *ph.ctr1 : 0) + index;
+  return ph.offsets[b] + static_cast<unsigned long long>(ph.offset_per_draw) * static_cast<unsigned long long>(draw);
+}
+__device__ __forceinline__ float philox_normal_at(unsigned long long seed, unsigned long long offset,
+                                                  unsigned threads, size_t l) {
+  const unsigned idx = static_cast<unsigned>(l % threads);
+  const size_t q = l / threads;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, idx, offset + 4ull * (q >> 2), &st);
+  const float4 n = curand_normal4(&st);
+  const unsigned c = static_cast<unsigned>(q & 3);
+  return c == 0 ? n.x : (c == 1 ? n.y : (c == 2 ? n.z : n.w));
+}
+
 __global__ void __launch_bounds__(256) sampler_update_kernel(const SamplerUpdate u) {
   const int b = blockIdx.y;
   const int row = (u.step_ptr ? *u.step_ptr : 0) * u.rows_per_step + b * u.row_batch_stride;
@@ -497,19 +516,30 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(const SamplerUpdate
   const float ux = cf[0], up = cf[1], kx = cf[2], k0 = cf[3], kn = cf[4];
   const float qa = u.known ? cf[5] : 0.f, qs = u.known ? cf[6] : 0.f;
   const size_t n4 = u.per_sample / 4;
+  const bool gen = u.ph.seeds != nullptr;
+  const unsigned long long seed = gen ? u.ph.seeds[b] : 0ull;
+  const unsigned long long off1 = gen ? philox_base_offset(u.ph, b, u.draw_noise) : 0ull;
+  const unsigned long long off2 = (gen && u.known) ? philox_base_offset(u.ph, b, u.draw_noise2) : 0ull;
   const float4* x = reinterpret_cast<const float4*>(u.x + b * u.per_sample);
   const float4* pr = reinterpret_cast<const float4*>(u.pred + b * u.per_sample);
-  const float4* nz = reinterpret_cast<const float4*>(u.noise + b * u.per_sample);
+  const float4* nz = gen ? nullptr : reinterpret_cast<const float4*>(u.noise + b * u.per_sample);
   const float4* kn4 = u.known ? reinterpret_cast<const float4*>(u.known + b * u.per_sample) : nullptr;
   const float4* mk = u.known ? reinterpret_cast<const float4*>(u.mask + b * u.per_sample) : nullptr;
-  const float4* n2 = u.known ? reinterpret_cast<const float4*>(u.noise2 + b * u.per_sample) : nullptr;
+  const float4* n2 = (u.known && !gen) ? reinterpret_cast<const float4*>(u.noise2 + b * u.per_sample) : nullptr;
   float4* xo = reinterpret_cast<float4*>(u.x_out + b * u.per_sample);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float4 xv = x[i], pv = pr[i], nv = nz[i];
+    const float4 xv = x[i], pv = pr[i];
     float xs[4] = {xv.x, xv.y, xv.z, xv.w};
     const float ps[4] = {pv.x, pv.y, pv.z, pv.w};
-    const float ns[4] = {nv.x, nv.y, nv.z, nv.w};
+    float ns[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!gen) {
+      const float4 nv = nz[i];
+      ns[0] = nv.x; ns[1] = nv.y; ns[2] = nv.z; ns[3] = nv.w;
+    } else if (kn != 0.f) {   // (deterministic DDIM: the reference draws and discards; only the offset advances)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ns[k] = philox_normal_at(seed, off1, u.ph.threads, 4 * i + k);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float x0 = fmaf(ux, xs[k], up * ps[k]);
@@ -517,9 +547,16 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(const SamplerUpdate
       xs[k] = fmaf(kx, xs[k], fmaf(k0, x0, kn * ns[k]));
     }
     if (kn4 != nullptr) {
-      const float4 kv = kn4[i], mv = mk[i], n2v = n2[i];
-      const float ks[4] = {kv.x, kv.y, kv.z, kv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w},
-                  n2s[4] = {n2v.x, n2v.y, n2v.z, n2v.w};
+      const float4 kv = kn4[i], mv = mk[i];
+      float n2s[4];
+      if (!gen) {
+        const float4 n2v = n2[i];
+        n2s[0] = n2v.x; n2s[1] = n2v.y; n2s[2] = n2v.z; n2s[3] = n2v.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) n2s[k] = philox_normal_at(seed, off2, u.ph.threads, 4 * i + k);
+      }
+      const float ks[4] = {kv.x, kv.y, kv.z, kv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float known_s = fmaf(qa, ks[k], qs * n2s[k]);
@@ -532,6 +569,7 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(const SamplerUpdate
 
 cudaError_t sampler_update_launch(const SamplerUpdate& u, cudaStream_t s) {
   if (u.per_sample % 4 != 0) return cudaErrorInvalidValue;
+  if (u.ph.seeds != nullptr && (u.ph.offsets == nullptr || u.ph.threads == 0)) return cudaErrorInvalidValue;
   const size_t n4 = u.per_sample / 4;
   int gx = static_cast<int>((n4 + 255) / 256);
   if (gx > 148 * 4) gx = 148 * 4;
@@ -543,27 +581,56 @@ cudaError_t sampler_update_launch(const SamplerUpdate& u, cudaStream_t s) {
 __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, const float* __restrict__ noise,
                                                     const float* __restrict__ ac, float* __restrict__ y,
                                                     size_t per_sample, const int* __restrict__ step_ptr,
-                                                    int rows_per_step, int row_batch_stride) {
+                                                    int rows_per_step, int row_batch_stride, const PhiloxDraw ph,
+                                                    int draw) {
   const int b = blockIdx.y;
   const int row = (step_ptr ? *step_ptr : 0) * rows_per_step + b * row_batch_stride;
   const float a = ac[2 * row], c = ac[2 * row + 1];
   const size_t n4 = per_sample / 4;
+  const bool gen = ph.seeds != nullptr;
+  const unsigned long long seed = gen ? ph.seeds[b] : 0ull;
+  const unsigned long long off = gen ? philox_base_offset(ph, b, draw) : 0ull;
   const float4* xv = reinterpret_cast<const float4*>(x + b * per_sample);
-  const float4* nv = reinterpret_cast<const float4*>(noise + b * per_sample);
+  const float4* nv = gen ? nullptr : reinterpret_cast<const float4*>(noise + b * per_sample);
   float4* yv = reinterpret_cast<float4*>(y + b * per_sample);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float4 p = xv[i], q = nv[i];
+    const float4 p = xv[i];
+    float4 q;
+    if (!gen) q = nv[i];
+    else q = make_float4(philox_normal_at(seed, off, ph.threads, 4 * i), philox_normal_at(seed, off, ph.threads, 4 * i + 1),
+                         philox_normal_at(seed, off, ph.threads, 4 * i + 2), philox_normal_at(seed, off, ph.threads, 4 * i + 3));
     yv[i] = make_float4(fmaf(a, p.x, c * q.x), fmaf(a, p.y, c * q.y), fmaf(a, p.z, c * q.z), fmaf(a, p.w, c * q.w));
   }
 }
 
 cudaError_t axpby_launch(const float* x, const float* noise, const float* ac, float* y, int B, size_t per_sample,
-                         const int* step_ptr, int rows_per_step, int row_batch_stride, cudaStream_t s) {
+                         const int* step_ptr, int rows_per_step, int row_batch_stride, cudaStream_t s,
+                         const PhiloxDraw* ph, int draw) {
   if (per_sample % 4 != 0) return cudaErrorInvalidValue;
   int gx = static_cast<int>((per_sample / 4 + 255) / 256);
   if (gx > 148 * 4) gx = 148 * 4;
-  axpby_kernel<<<dim3(gx, B), 256, 0, s>>>(x, noise, ac, y, per_sample, step_ptr, rows_per_step, row_batch_stride);
+  PhiloxDraw none;
+  memset(&none, 0, sizeof(none));
+  axpby_kernel<<<dim3(gx, B), 256, 0, s>>>(x, noise, ac, y, per_sample, step_ptr, rows_per_step, row_batch_stride,
+                                           ph ? *ph : none, draw);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, const PhiloxDraw ph, int draw,
+                                                            size_t per_sample) {
+  const int b = blockIdx.y;
+  const unsigned long long seed = ph.seeds[b], off = philox_base_offset(ph, b, draw);
+  for (size_t l = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; l < per_sample;
+       l += static_cast<size_t>(gridDim.x) * blockDim.x)
+    out[b * per_sample + l] = philox_normal_at(seed, off, ph.threads, l);
+}
+
+cudaError_t philox_normal_launch(float* out, const PhiloxDraw& ph, int draw, int B, size_t per_sample, cudaStream_t s) {
+  if (ph.seeds == nullptr || ph.offsets == nullptr || ph.threads == 0) return cudaErrorInvalidValue;
+  int gx = static_cast<int>((per_sample + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  philox_normal_kernel<<<dim3(gx, B), 256, 0, s>>>(out, ph, draw, per_sample);
   return cudaGetLastError();
 }
 

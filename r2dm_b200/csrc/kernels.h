@@ -9,6 +9,17 @@ namespace r2dm {
 constexpr int kNU = 8;  // GroupNorm statistic units per tensor (= gn_num_groups of the reference)
 
 enum DType : int { kF32 = 0, kBF16 = 1 };
+
+// cudaFuncSetAttribute and the SM count are per device: a launcher keeps one bit per device ordinal
+// (one process may drive several GPUs, e.g. a model moved from cuda:0 to cuda:1).
+inline bool first_use_on_this_device(unsigned long long& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  const bool first = (mask & bit) == 0;
+  mask |= bit;
+  return first;
+}
 inline int dtype_size(int dt) { return dt == kBF16 ? 2 : 4; }
 inline int dtype_cw(int dt) { return 16 / dtype_size(dt); }
 
@@ -40,7 +51,6 @@ struct ConvLaunch {
   int dtype;          // kF32 (tf32 tensor cores) or kBF16
   int taps;           // 9 (3x3 ring conv) or 1 (1x1 conv / linear over tokens)
   int nt, ht;         // N tile (output channels per CTA) and output rows per tile
-  int pair;           // nt == 128 only: CTA-pair kernel (two rows per CTA, M = 256 over two CTAs); nt == 256 implies it
   PT in0, in1;        // input(s); in1.ptr == nullptr unless the input is a channel concat
   int cin_pad;        // total input channels incl. zero padding (multiple of the stage K)
   const void* wpacked;  // packed weights (pack_conv_weight)
@@ -51,6 +61,7 @@ struct ConvLaunch {
   float scale;        // applied after bias (+ residual)
   float* out_nchw;    // if non-null: write fp32 [B][cout][H][W] instead of `out`
   ConvXform xf;       // fused input normalisation (enabled = 0: plain convolution)
+  int reverse;        // tile order back to front (alternated between consecutive launches, see conv_umma.cu)
   CUtensorMap tmap0, tmap1;
 };
 // Fills l.tmap0/tmap1 for the current in0/in1 pointers.  Returns 0 on success.
@@ -59,11 +70,14 @@ int conv_stage_channels(int dtype, int taps);  // K per pipeline stage
 size_t conv_packed_weight_bytes(int dtype, int taps, int nt, int cin_pad, int cout_pad);
 int conv_stat_slots(const ConvLaunch& l);
 cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s);
+// process-wide developer options (r2dm_set_option / R2DM_OPT_<NAME> in the environment)
+int get_option(const char* name, int dflt);
+int set_option(const char* name, int value);
 // developer timeline of CTA 0 of subsequent conv launches: buf[4 roles][cap] (globaltimer ns), or null
 void conv_set_trace(unsigned long long* buf, int cap);
 // w: fp32 [cout][cin][k][k] (OIHW), k*k == taps
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin,
-                             int cin_pad, int cout_pad, void* dst, cudaStream_t s, int pair = 0);
+                             int cin_pad, int cout_pad, void* dst, cudaStream_t s);
 
 // ------------------------------------------------------------------ layout conversion
 cudaError_t pack_nchw(int dtype, const float* src, int B, int Csrc, int H, int W, PT dst,
@@ -122,6 +136,19 @@ cudaError_t cond_embed_launch(const CondEmbed& c, cudaStream_t s);
 // x0 = clamp(ux*x + up*pred); x' = kx*x + k0*x0 + kn*noise ; coef rows of 5 floats, row index =
 // step*rows_per_step + b*row_batch_stride.  Optional RePaint blend with the re-noised known image:
 // x' = mask*(qa*known + qs*noise2) + (1-mask)*x'   (coef row has 7 floats then).
+// Noise drawn inside the kernel, bit-identical to torch.randn(per_sample elements, generator=cuda_gen_b)
+// (models/diffusion/base.py:71-94 with a list of per-sample CUDA generators): element l of the tensor is
+// component (l / threads) % 4 of curand_normal4 of the Philox4x32-10 stream (seed_b, subsequence
+// l % threads, offset_b + offset_per_draw * draw + 4 * (l / threads / 4)), exactly what ATen's
+// distribution_nullary_kernel computes for its launch width `threads`.
+struct PhiloxDraw {
+  const unsigned long long* seeds;    // [B] device; null = noise comes from memory
+  const unsigned long long* offsets;  // [B] device: generator offset before the first draw of the loop
+  const int* ctr0; const int* ctr1;   // draw number = mul0 * *ctr0 + mul1 * *ctr1 + index (null -> 0)
+  int mul0, mul1;
+  unsigned offset_per_draw, threads;
+};
+
 struct SamplerUpdate {
   float* x; const float* pred; const float* noise;
   const float* coef; int coef_cols;
@@ -130,13 +157,18 @@ struct SamplerUpdate {
   const float* known; const float* mask; const float* noise2;  // RePaint (or null)
   float* x_out;        // may alias x
   int B; size_t per_sample;
+  PhiloxDraw ph;       // ph.seeds != null: noise / noise2 are generated (draw indices below), not read
+  int draw_noise, draw_noise2;
 };
 cudaError_t sampler_update_launch(const SamplerUpdate& u, cudaStream_t s);
 // y = a*x + c*noise  (q_step / q_step_from_x_0), coefficients on device: ac[row][2],
 // row = step*rows_per_step + b*row_batch_stride (step_ptr may be null -> 0)
 cudaError_t axpby_launch(const float* x, const float* noise, const float* ac, float* y, int B,
                          size_t per_sample, const int* step_ptr, int rows_per_step, int row_batch_stride,
-                         cudaStream_t s);
+                         cudaStream_t s, const PhiloxDraw* ph = nullptr, int draw = 0);
+// out[b] = the `draw`-th torch.randn of sample b's generator (tests, x_T)
+cudaError_t philox_normal_launch(float* out, const PhiloxDraw& ph, int draw, int B, size_t per_sample,
+                                 cudaStream_t s);
 cudaError_t advance_step_launch(int* step_ptr, int delta, cudaStream_t s);
 // [depth, x, y, z, reflectance] from a sample in [-1, 1] (sample_and_save.py:52-57)
 cudaError_t lidar_postprocess_launch(const float* sample, const float* angles, float* out, int B,

@@ -35,7 +35,6 @@ inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 struct ConvW {
   std::string name;
   int taps = 9, cin = 0, cout = 0, cin_pad = 0, cout_pad = 0, nt = 64;
-  int pair = 0;   // nt == 128 on the CTA-pair kernel (option pair = 2)
   size_t w_off = 0, b_off = 0;
   bool w_ok = false, b_ok = false;
 };
@@ -107,25 +106,32 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
   return static_cast<int>(m->raws.size()) - 1;
 }
 
-// CTA-pair kernels (R2DM_PAIR / r2dm_set_option("pair", v)): 0 = off, 1 = 256-channel pairs (one row per
-// CTA) for layers with a multiple of 256 output channels, 2 = 128-channel pairs (two rows per CTA, six-slot
-// ring) for every 3x3 layer with a multiple of 128 output channels.  See DESIGN.md for the measurements.
-static int g_pair = -1;
-static int pair_mode() {
-  if (g_pair < 0) { const char* e = getenv("R2DM_PAIR"); g_pair = e ? atoi(e) : 0; }
-  return g_pair;
+}  // namespace
+namespace r2dm {
+// Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
+static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles"};
+int get_option(const char* name, int dflt) {
+  auto& m = option_map();
+  auto it = m.find(name);
+  if (it != m.end()) return it->second;
+  std::string env = "R2DM_OPT_";
+  for (const char* c = name; *c; ++c) env += static_cast<char>(toupper(*c));
+  const char* e = getenv(env.c_str());
+  const int v = e ? atoi(e) : dflt;
+  m[name] = v;
+  return v;
 }
-static bool pair_enabled() { return pair_mode() == 1; }
-// 128-channel pairs need tiles of 4 rows per pair
-static bool pair128(int taps, int cout, int dtype, bool rows_mult4) {
-  return pair_mode() == 2 && taps == 9 && dtype == kBF16 && cout % 128 == 0 && rows_mult4;
+int set_option(const char* name, int value) {
+  for (const char* n : kOptionNames)
+    if (std::string(n) == name) { option_map()[name] = value; return 0; }
+  return -1;
 }
-
-// N tile: 256 selects the CTA-pair kernel (bf16 3x3 convolutions with a multiple of 256 output channels
-// on tensors with an even number of rows), else 128 / 64 / 16 output channels per single-CTA tile
-int pick_nt(int taps, int cout, int dtype, bool even_rows) {
+}  // namespace r2dm
+namespace {
+// N tile: 128 / 64 / 16 output channels per tile
+int pick_nt(int cout) {
   if (cout <= 16) return 16;
-  if (taps == 9 && dtype == kBF16 && cout % 256 == 0 && even_rows && pair_enabled()) return 256;
   return cout % 128 == 0 ? 128 : 64;
 }
 
@@ -133,8 +139,7 @@ int add_conv(r2dm_model* m, const std::string& name, int taps, int cin, int cout
   ConvW c;
   c.name = name;
   c.taps = taps; c.cin = cin; c.cout = cout;
-  c.nt = pick_nt(taps, cout, m->dtype, m->cfg.height % 16 == 0);   // every level then has an even height
-  c.pair = pair128(taps, cout, m->dtype, m->cfg.height % 32 == 0) ? 1 : 0;   // ... a multiple of 4
+  c.nt = pick_nt(cout);
   c.cin_pad = round_up(cin, conv_stage_channels(m->dtype, taps));
   c.cout_pad = round_up(cout, c.nt);
   c.w_off = m->arena_bytes;
@@ -252,6 +257,7 @@ struct Builder {
   Planner pl;
   std::vector<Op> prog;
   std::map<std::string, PT> named;
+  int n_convs = 0;
 
   const PT& T(int id) const { return pl.tensors[id]; }
 
@@ -268,22 +274,25 @@ struct Builder {
     op.is_output = is_output;
     ConvLaunch& l = op.conv;
     memset(&l, 0, sizeof(l));
-    l.dtype = m->dtype; l.taps = w.taps; l.nt = w.nt; l.pair = w.pair;
-    if (w.taps == 9) l.ht = (w.nt == 256) ? 1 : (w.nt == 128) ? (a.H >= 2 ? 2 : 1) : (a.H % 4 == 0 ? 4 : (a.H >= 2 ? 2 : 1));
+    l.dtype = m->dtype; l.taps = w.taps; l.nt = w.nt;
+    if (w.taps == 9) l.ht = (w.nt == 128) ? (a.H >= 2 ? 2 : 1) : (a.H % 4 == 0 ? 4 : (a.H >= 2 ? 2 : 1));
     else l.ht = a.H >= 2 ? 2 : 1;
     if (w.nt == 16 && l.ht != 4) l.ht = 4;
     // low-resolution levels: with two-row tiles fewer than half of the 148 SMs would get a tile, so
     // halve the tile (the persistent grid then covers twice as many SMs with half the K loop each)
-    if (w.taps == 9 && w.nt == 128 && l.ht == 2 && !w.pair) {
+    if (w.taps == 9 && w.nt == 128 && l.ht == 2) {
       // (decided per image, never from the batch size: the accumulation order depends on the tile
       //  shape and results must not depend on the batch composition)
       const int tiles_per_image = (a.H / 2) * (a.W / 128) * (w.cout_pad / 128);
-      if (tiles_per_image <= 9) l.ht = 1;
+      if (tiles_per_image <= get_option("ht1_max_tiles", 9)) l.ht = 1;
     }
     l.in0 = a;
     if (in1 >= 0) l.in1 = T(in1);
     l.cin_pad = w.cin_pad; l.cout = w.cout; l.cout_pad = w.cout_pad;
     l.scale = scale;
+    // consecutive convolutions walk their tiles in opposite directions (L2 reuse of the previous output)
+    l.reverse = get_option("serpentine", 1) ? (n_convs & 1) : 0;
+    ++n_convs;
     int out_id = -1;
     if (!is_output) {
       int slots = 0;
@@ -514,7 +523,7 @@ int r2dm_load_tensor(r2dm_handle h, const char* name_c, const float* src, const 
       if (n != static_cast<size_t>(c.cout) * c.cin * c.taps)
         return fail(-3, "%s: expected %d x %d x %d elements, got %zu", name_c, c.cout, c.cin, c.taps, n);
       CUDA_TRY(pack_conv_weight(h->dtype, c.taps, c.nt, src, c.cout, c.cin, c.cin_pad, c.cout_pad,
-                                h->arena + c.w_off, s, c.pair));
+                                h->arena + c.w_off, s));
       c.w_ok = true;
     } else {
       if (n != static_cast<size_t>(c.cout)) return fail(-3, "%s: expected %d elements, got %zu", name_c, c.cout, n);
@@ -761,7 +770,58 @@ int r2dm_sampler_update(float* x_out, const float* x, const float* pred, const f
   u.step_ptr = step_ptr; u.rows_per_step = rows_per_step; u.row_batch_stride = row_batch_stride;
   u.clip = clip; u.known = known; u.mask = mask; u.noise2 = noise2; u.x_out = x_out;
   u.B = batch; u.per_sample = per_sample;
+  memset(&u.ph, 0, sizeof(u.ph)); u.draw_noise = u.draw_noise2 = 0;
   CUDA_TRY(sampler_update_launch(u, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+static int to_philox(const r2dm_philox* p, PhiloxDraw* out) {
+  if (!p || !p->seeds || !p->offsets) return fail(-1, "philox: null seeds / offsets");
+  if (p->threads == 0 || p->offset_per_draw == 0) return fail(-1, "philox: threads / offset_per_draw must be > 0");
+  out->seeds = reinterpret_cast<const unsigned long long*>(p->seeds);
+  out->offsets = reinterpret_cast<const unsigned long long*>(p->offsets);
+  out->ctr0 = p->ctr0; out->ctr1 = p->ctr1; out->mul0 = p->mul0; out->mul1 = p->mul1;
+  out->offset_per_draw = p->offset_per_draw; out->threads = p->threads;
+  return 0;
+}
+
+int r2dm_sampler_update_philox(float* x_out, const float* x, const float* pred, const float* coef, int coef_cols,
+                               const int* step_ptr, int rows_per_step, int row_batch_stride, float clip,
+                               const float* known, const float* mask, const r2dm_philox* philox, int draw_noise,
+                               int draw_noise2, int batch, size_t per_sample, void* stream) {
+  if (!x_out || !x || !pred || !coef) return fail(-1, "null argument");
+  if (coef_cols < (known ? 7 : 5)) return fail(-1, "coef_cols too small");
+  if (known && !mask) return fail(-1, "RePaint blend needs a mask");
+  SamplerUpdate u;
+  u.x = const_cast<float*>(x); u.pred = pred; u.noise = nullptr; u.coef = coef; u.coef_cols = coef_cols;
+  u.step_ptr = step_ptr; u.rows_per_step = rows_per_step; u.row_batch_stride = row_batch_stride;
+  u.clip = clip; u.known = known; u.mask = mask; u.noise2 = nullptr; u.x_out = x_out;
+  u.B = batch; u.per_sample = per_sample;
+  int rc = to_philox(philox, &u.ph);
+  if (rc) return rc;
+  u.draw_noise = draw_noise; u.draw_noise2 = draw_noise2;
+  CUDA_TRY(sampler_update_launch(u, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_axpby_table_philox(float* y, const float* x, const float* table, const int* step_ptr, int rows_per_step,
+                            int row_batch_stride, const r2dm_philox* philox, int draw, int batch,
+                            size_t per_sample, void* stream) {
+  if (!y || !x || !table) return fail(-1, "null argument");
+  PhiloxDraw ph;
+  int rc = to_philox(philox, &ph);
+  if (rc) return rc;
+  CUDA_TRY(axpby_launch(x, nullptr, table, y, batch, per_sample, step_ptr, rows_per_step, row_batch_stride,
+                        static_cast<cudaStream_t>(stream), &ph, draw));
+  return 0;
+}
+
+int r2dm_philox_normal(float* out, const r2dm_philox* philox, int draw, int batch, size_t per_sample, void* stream) {
+  if (!out) return fail(-1, "null argument");
+  PhiloxDraw ph;
+  int rc = to_philox(philox, &ph);
+  if (rc) return rc;
+  CUDA_TRY(philox_normal_launch(out, ph, draw, batch, per_sample, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 
@@ -829,11 +889,10 @@ int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const floa
   ConvLaunch l;
   memset(&l, 0, sizeof(l));
   l.dtype = dtype; l.taps = taps;
-  l.nt = pick_nt(taps, Cout, dtype, H % 2 == 0);
-  l.pair = (l.nt == 128 && pair128(taps, Cout, dtype, H % 4 == 0)) ? 1 : 0;
+  l.nt = pick_nt(Cout);
   l.cin_pad = round_up(Cin, conv_stage_channels(dtype, taps));
   l.cout = Cout; l.cout_pad = round_up(Cout, l.nt);
-  if (taps == 9) l.ht = (l.nt == 256) ? 1 : (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
+  if (taps == 9) l.ht = (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
   else l.ht = H >= 2 ? 2 : 1;
   if (l.nt == 16 && l.ht != 4) return fail(-1, "small-N conv needs H %% 4 == 0");
   l.in0 = make_pt(sc, dtype, B, l.cin_pad, H, W, 0);
@@ -844,7 +903,7 @@ int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const floa
   if (!l.in0.ptr || !l.out.ptr || !res.ptr || !wp || !bp) return fail(-1, "scratch too small");
   CUDA_TRY(cudaMemsetAsync(l.in0.ptr, 0, l.in0.bytes(dtype), s));
   CUDA_TRY(pack_nchw(dtype, x, B, Cin, H, W, l.in0, 0, s));
-  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s, l.pair));
+  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s));
   CUDA_TRY(cudaMemsetAsync(bp, 0, static_cast<size_t>(l.cout_pad) * 4, s));
   if (bias) CUDA_TRY(cudaMemcpyAsync(bp, bias, static_cast<size_t>(Cout) * 4, cudaMemcpyDeviceToDevice, s));
   if (residual) {
@@ -872,12 +931,11 @@ int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, con
   ConvLaunch l;
   memset(&l, 0, sizeof(l));
   l.dtype = dtype; l.taps = taps;
-  l.nt = pick_nt(taps, Cout, dtype, H % 2 == 0);
-  l.pair = (l.nt == 128 && pair128(taps, Cout, dtype, H % 4 == 0)) ? 1 : 0;
+  l.nt = pick_nt(Cout);
   l.cin_pad = round_up(Cin, conv_stage_channels(dtype, taps));
   if (l.cin_pad != Cin) return fail(-1, "Cin must be a multiple of the stage K (%d)", conv_stage_channels(dtype, taps));
   l.cout = Cout; l.cout_pad = round_up(Cout, l.nt);
-  if (taps == 9) l.ht = (l.nt == 256) ? 1 : (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
+  if (taps == 9) l.ht = (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
   else l.ht = H >= 2 ? 2 : 1;
   PT probe; probe.B = B; probe.C = Cin; probe.H = H; probe.W = W;
   l.in0 = make_pt(sc, dtype, B, Cin, H, W, tensor_stats_slots(dtype, probe));
@@ -888,7 +946,7 @@ int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, con
   // NOTE: the input is stored unrounded here (it is a residual-stream tensor in the network)
   CUDA_TRY(pack_nchw(dtype, x, B, Cin, H, W, l.in0, 0, s));
   CUDA_TRY(tensor_stats_launch(dtype, l.in0, s));
-  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s, l.pair));
+  CUDA_TRY(pack_conv_weight(dtype, taps, l.nt, w, Cout, Cin, l.cin_pad, l.cout_pad, wp, s));
   CUDA_TRY(cudaMemsetAsync(bp, 0, static_cast<size_t>(l.cout_pad) * 4, s));
   if (bias) CUDA_TRY(cudaMemcpyAsync(bp, bias, static_cast<size_t>(Cout) * 4, cudaMemcpyDeviceToDevice, s));
   l.wpacked = wp; l.bias = bp; l.scale = 1.f;
@@ -964,7 +1022,7 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
 }
 
 int r2dm_set_option(const char* name, int value) {
-  if (name && std::string(name) == "pair") { g_pair = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }
+  if (name && set_option(name, value) == 0) return 0;
   return fail(-1, "unknown option %s", name ? name : "(null)");
 }
 

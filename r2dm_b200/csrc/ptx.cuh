@@ -224,74 +224,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 
-// ----------------------------------------------------------------------------- clusters / CTA pairs
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-// all threads of every CTA of the cluster
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `bar` in CTA `rank` of this cluster
-__device__ __forceinline__ uint32_t mapa_u32(const void* local, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
-  return r;
-}
-// arrive on an mbarrier that may live in the peer CTA; cluster-scope release so that everything this
-// thread observed or wrote before (the landed TMA data, its own transformed tile) is visible to the waiter
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// TMEM allocation for a CTA pair: the same warp of BOTH CTAs executes it (same smem slot offset)
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(kCols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <uint32_t kCols>
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
-}
-// D[tmem of both CTAs] (+)= A * B across a CTA pair (M = 256: 128 rows per CTA; each CTA supplies half of
-// the N rows of B from its own shared memory).  Whole warp of the LEADER CTA calls it, one lane issues.
-__device__ __forceinline__ void umma_f16_pair_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                                   uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-      :
-      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-// commit of the pair's MMAs: arrives on the barrier at this shared-memory offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_pair_warp(uint64_t* bar) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
-      "mov.b16 m, 3;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
-      ::"r"(smem_u32(bar))
-      : "memory");
-}
-
 // ----------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (tcgen05), see DESIGN.md "UMMA operand layouts".
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4

@@ -14,9 +14,13 @@ How the hot loop runs (no host sync between steps):
     on the host, in fp64, into a coefficient table [N, 5(+2)];
   * one step = U-Net forward + fused update + counter increment, captured once in a CUDA graph and
     replayed N times; the kernels pick their table row through a device-side step counter;
-  * noise is drawn exactly like the reference does (`torch.randn(C,H,W, generator=g_i)` per sample
-    per step, base.py:71-94) straight into the graph's static noise buffer, so the RNG stream is
-    identical to the reference's on the same device type.
+  * noise: with `rng` = a list of per-sample CUDA generators on the model's device (what
+    utils/inference.py:113-114 builds) the draws happen INSIDE the update kernel - Philox4x32-10 +
+    Box-Muller laid out like ATen's normal_ kernel, bit-identical to the reference's
+    `torch.randn(C,H,W, generator=g_i)` per sample per step (base.py:71-94) - and the generators'
+    offsets are advanced on the host afterwards, so the whole loop is graph replays with nothing in
+    between.  Any other `rng` (None, one generator, CPU generators) is drawn on the host exactly like
+    the reference does, into the graph's static noise buffer.
 """
 from __future__ import annotations
 
@@ -98,6 +102,40 @@ def continuous_coefficients(lam_t: torch.Tensor, lam_s: torch.Tensor, mode: str,
     return torch.stack([ux, up, kx, k0, kn], dim=1)
 
 
+# ------------------------------------------------------------------------------------- device noise
+def _torch_randn_geometry(numel: int, device) -> tuple:
+    """(threads, offset_per_draw) of ATen's CUDA normal_ kernel for a tensor of `numel` elements
+    (ATen/native/cuda/DistributionTemplates.h, distribution_nullary_kernel: block 256, unroll 4, grid
+    capped at SMs * maxThreadsPerSM / 256; every call advances the Philox offset by
+    ceil(numel / (threads * 4)) * 4)."""
+    props = torch.cuda.get_device_properties(device)
+    block, unroll = 256, 4
+    grid = min((numel + block - 1) // block,
+               props.multi_processor_count * (props.max_threads_per_multi_processor // block))
+    threads = grid * block
+    return threads, ((numel - 1) // (threads * unroll) + 1) * 4
+
+
+def _cuda_gen_seed_offset(g: torch.Generator) -> tuple:
+    """(seed, philox offset) of a CUDA generator (state = two little-endian uint64)."""
+    st = g.get_state()
+    assert st.numel() == 16, "unexpected CUDA generator state layout"
+    v = st.view(torch.int64)
+    return int(v[0].item()) & (2 ** 64 - 1), int(v[1].item()) & (2 ** 64 - 1)
+
+
+def _cuda_gen_advance(g: torch.Generator, delta: int) -> None:
+    st = g.get_state().clone()
+    v = st.view(torch.int64)
+    off = ((int(v[1].item()) & (2 ** 64 - 1)) + delta) & (2 ** 64 - 1)
+    v[1] = off - 2 ** 64 if off >= 2 ** 63 else off
+    g.set_state(st)
+
+
+def _u64_tensor(vals, device) -> torch.Tensor:
+    return torch.tensor([v - 2 ** 64 if v >= 2 ** 63 else v for v in vals], dtype=torch.int64, device=device)
+
+
 # ------------------------------------------------------------------------------------- base
 class GaussianDiffusion(nn.Module):
     """Mirror of models/diffusion/base.py:9-163 (sampling members only)."""
@@ -138,7 +176,9 @@ class GaussianDiffusion(nn.Module):
             assert hasattr(self.model, "in_channels")
             self.sampling_shape = (self.model.in_channels, *sampling_resolution)
         self.use_cuda_graph = True
-        self.graph_steps = 8   # denoising steps captured per CUDA graph in sample()
+        self.graph_steps = 8   # denoising steps captured per CUDA graph in sample() (host-drawn noise)
+        self.graph_steps_device_noise = 16   # ... when the noise is drawn inside the update kernel
+        self.device_noise = True   # False: always draw on the host (debugging / A-B tests)
         self._graphs = {}
         self.setup_parameters()
         self.register_buffer("_dummy", torch.tensor([]))
@@ -198,6 +238,32 @@ class GaussianDiffusion(nn.Module):
     def _clip(self) -> float:
         return float(self.clip_sample_range) if self.clip_sample else 0.0
 
+    def _device_noise_ok(self, rng, dev) -> bool:
+        return (bool(getattr(self, "device_noise", True)) and isinstance(rng, list) and len(rng) > 0
+                and dev.type == "cuda" and all(isinstance(r, torch.Generator) and r.device == dev for r in rng))
+
+    def _philox(self, st, rng, per, dev, ctr0=None, mul0=0, ctr1=None, mul1=0):
+        """Fill the loop state's static seed / offset tensors from the generators' CURRENT state and
+        return (r2dm_philox struct, offset_per_draw)."""
+        so = [_cuda_gen_seed_offset(r) for r in rng]
+        st["seeds"].copy_(_u64_tensor([a for a, _ in so], dev))
+        st["offsets"].copy_(_u64_tensor([b for _, b in so], dev))
+        threads, inc = _torch_randn_geometry(per, dev)
+        ph = L.R2dmPhilox(L.ptr(st["seeds"]), L.ptr(st["offsets"]), L.ptr(ctr0) if ctr0 is not None else None,
+                          L.ptr(ctr1) if ctr1 is not None else None, mul0, mul1, inc, threads)
+        return ph, inc
+
+    def _update_philox(self, x_out, x, pred, coef, step_ptr, rows_per_step, row_batch_stride, ph,
+                       draw_noise=0, draw_noise2=0, known=None, mask=None):
+        import ctypes
+        L.check(L.lib().r2dm_sampler_update_philox(
+            L.ptr(x_out), L.ptr(x), L.ptr(pred), L.ptr(coef), coef.shape[1],
+            L.ptr(step_ptr) if step_ptr is not None else None, rows_per_step, row_batch_stride, self._clip(),
+            L.ptr(known) if known is not None else None, L.ptr(mask) if mask is not None else None,
+            ctypes.byref(ph), draw_noise, draw_noise2, x.shape[0], x[0].numel(), L.stream_ptr()),
+            "r2dm_sampler_update_philox")
+        return x_out
+
     def _update(self, x_out, x, pred, noise, coef, step_ptr, rows_per_step, row_batch_stride,
                 known=None, mask=None, noise2=None):
         B = x.shape[0]
@@ -227,9 +293,11 @@ class GaussianDiffusion(nn.Module):
         B = x.shape[0]
         with torch.cuda.device(dev):
             lib = L.lib()
-            K = 1 if return_all else max(1, int(getattr(self, "graph_steps", 8)))
+            philox = draw_noise and self._device_noise_ok(rng, dev)
+            K = 1 if return_all else max(1, int(getattr(self, "graph_steps_device_noise", 16) if philox
+                                                else getattr(self, "graph_steps", 8)))
             ncoef = coefs.shape[1]
-            key = (B, K, ncoef, self._clip(), tuple(x.shape[1:]))
+            key = (B, K, ncoef, self._clip(), tuple(x.shape[1:]), philox)
             eng.bind(B)
             st = getattr(self, "_loop_state", None)
             if (st is None or st["key"] != key or st["eng"] is not eng or st["epoch"] != eng.bind_epoch
@@ -238,7 +306,10 @@ class GaussianDiffusion(nn.Module):
                     "key": key, "eng": eng, "epoch": eng.bind_epoch,
                     "x": torch.empty((B,) + tuple(x.shape[1:]), device=dev, dtype=torch.float32),
                     "pred": torch.empty((B,) + tuple(x.shape[1:]), device=dev, dtype=torch.float32),
-                    "noise": torch.zeros((K, B) + tuple(x.shape[1:]), device=dev, dtype=torch.float32),
+                    "noise": torch.zeros((1 if philox else K, B) + tuple(x.shape[1:]), device=dev,
+                                         dtype=torch.float32),
+                    "seeds": torch.zeros(B, dtype=torch.int64, device=dev),
+                    "offsets": torch.zeros(B, dtype=torch.int64, device=dev),
                     "film": torch.zeros(max(N, 256), eng.film_width, device=dev, dtype=torch.float32),
                     "coef": torch.zeros(max(N, 256), ncoef, device=dev, dtype=torch.float32),
                     "step": torch.zeros(1, dtype=torch.int32, device=dev),
@@ -252,15 +323,23 @@ class GaussianDiffusion(nn.Module):
             step.zero_()
             if not draw_noise:
                 noise.zero_()
+            ph = None
+            if philox:
+                # draw number of step i is i (one draw per step; the x_T draw has already been consumed)
+                ph, inc = self._philox(st, rng, xs[0].numel(), dev, ctr0=step, mul0=1)
+                st["ph"] = ph   # keeps the struct alive; graphs hold only the device pointers inside it
             out = [xs.clone()] if return_all else None
 
             def one_step(k=0):
                 eng.forward_film(xs, st["film"], pred, step_ptr=step, rows_per_step=1, row_batch_stride=0)
-                self._update(xs, xs, pred, noise[k], st["coef"], step, 1, 0)
+                if philox:
+                    self._update_philox(xs, xs, pred, st["coef"], step, 1, 0, ph)
+                else:
+                    self._update(xs, xs, pred, noise[k], st["coef"], step, 1, 0)
                 L.check(lib.r2dm_advance_step(L.ptr(step), 1, L.stream_ptr()))
 
             def draw(n):
-                if draw_noise:
+                if draw_noise and not philox:
                     for k in range(n):
                         self.randn_like(xs, rng=rng, out=noise[k])
 
@@ -295,6 +374,9 @@ class GaussianDiffusion(nn.Module):
                 if return_all:
                     out.append(xs.clone())
             bar.close()
+            if philox:   # leave the generators where N host-side draws would have left them
+                for r in rng:
+                    _cuda_gen_advance(r, N * inc)
         return torch.stack(out) if return_all else xs.clone()
 
 
@@ -459,15 +541,32 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
             qstep = torch.zeros(1, dtype=torch.int32, device=dev)
             pred, noise, noise2 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
             per = x[0].numel()
+            philox = self._device_noise_ok(rng, dev)
+            if philox:
+                # draws so far = 2 per reverse step (known-region noise first, then the p_step noise,
+                # continuous_time.py:296-299) + 1 per re-noising step
+                pst = {"seeds": torch.zeros(batch_size, dtype=torch.int64, device=dev),
+                       "offsets": torch.zeros(batch_size, dtype=torch.int64, device=dev)}
+                ph, inc = self._philox(pst, rng, per, dev, ctr0=pstep, mul0=2, ctr1=qstep, mul1=1)
 
             def reverse_step():
                 eng.forward_film(x, film, pred, step_ptr=pstep, rows_per_step=1, row_batch_stride=0)
-                self._update(x, x, pred, noise, coef, pstep, 1, 0, known, mask, noise2)
+                if philox:
+                    self._update_philox(x, x, pred, coef, pstep, 1, 0, ph, draw_noise=1, draw_noise2=0,
+                                        known=known, mask=mask)
+                else:
+                    self._update(x, x, pred, noise, coef, pstep, 1, 0, known, mask, noise2)
                 L.check(lib.r2dm_advance_step(L.ptr(pstep), 1, L.stream_ptr()))
 
             def renoise_step():
-                L.check(lib.r2dm_axpby_table(L.ptr(x), L.ptr(x), L.ptr(noise), L.ptr(qtab), L.ptr(qstep), 1, 0,
-                                             batch_size, per, L.stream_ptr()), "r2dm_axpby_table")
+                if philox:
+                    import ctypes
+                    L.check(lib.r2dm_axpby_table_philox(L.ptr(x), L.ptr(x), L.ptr(qtab), L.ptr(qstep), 1, 0,
+                                                        ctypes.byref(ph), 0, batch_size, per, L.stream_ptr()),
+                            "r2dm_axpby_table_philox")
+                else:
+                    L.check(lib.r2dm_axpby_table(L.ptr(x), L.ptr(x), L.ptr(noise), L.ptr(qtab), L.ptr(qstep), 1, 0,
+                                                 batch_size, per, L.stream_ptr()), "r2dm_axpby_table")
                 L.check(lib.r2dm_advance_step(L.ptr(qstep), 1, L.stream_ptr()))
 
             graphs = {"p": None, "q": None}
@@ -480,9 +579,10 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
                     if return_all:
                         out.append(x.clone())
                     continue
-                if op == "p":
-                    self.randn_like(x, rng=rng, out=noise2)     # q_step_from_x_0(known) draw
-                self.randn_like(x, rng=rng, out=noise)
+                if not philox:
+                    if op == "p":
+                        self.randn_like(x, rng=rng, out=noise2)     # q_step_from_x_0(known) draw
+                    self.randn_like(x, rng=rng, out=noise)
                 if graphs[op] is not None:
                     graphs[op].replay()
                     continue
@@ -494,6 +594,10 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
                     with torch.cuda.graph(g):
                         fns[op]()
                     graphs[op] = g
+            if philox:
+                n_q = sum(1 for o in prog if o == "q")
+                for r in rng:
+                    _cuda_gen_advance(r, (2 * n_p + n_q) * inc)
         return torch.stack(out) if return_all else x
 
 

@@ -155,41 +155,3 @@ def test_fused_groupnorm_conv(case, dtype):
     e = rel_l2(y, ref)
     tol = 6e-3 if dtype == "bf16" else 1e-3
     assert e <= tol, f"fused gn+conv {case}[{dtype}]: l2-rel {e:.3e} > {tol}"
-
-
-# ------------------------------------------------------------------------------------------ CTA pairs
-@pytest.fixture(params=[1, 2], ids=["pair256", "pair128"])
-def pair_kernel(request):
-    """Select the thread-block-cluster kernels (two CTAs, tcgen05.mma.cta_group::2): mode 1 = one row x 256
-    channels per CTA for layers with a multiple of 256 output channels, mode 2 = two rows x 128 channels per
-    CTA (six-slot ring) for a multiple of 128; off by default."""
-    from r2dm_b200 import _lib
-    _lib.check(_lib.lib().r2dm_set_option(b"pair", request.param), "set_option")
-    yield
-    _lib.check(_lib.lib().r2dm_set_option(b"pair", 0), "set_option")
-
-
-@pytest.mark.parametrize("case", [(2, 128, 256, 4, 256, 3, True), (1, 64, 512, 4, 128, 3, False),
-                                  (3, 256, 256, 8, 128, 3, True), (2, 64, 128, 8, 256, 3, False)])
-def test_conv_cta_pair(pair_kernel, case):
-    test_conv(case, "bf16")
-
-
-@pytest.mark.parametrize("case", [(2, 256, 256, 4, 128, 3, True), (1, 128, 512, 8, 256, 3, False),
-                                  (2, 512, 512, 4, 128, 3, True), (2, 128, 128, 8, 256, 3, True)])
-def test_fused_groupnorm_conv_cta_pair(pair_kernel, case):
-    test_fused_groupnorm_conv(case, "bf16")
-
-
-def test_cta_pair_matches_single_cta_kernel(pair_kernel):
-    """Same inputs through both kernels: identical products, different summation order only."""
-    from r2dm_b200 import _lib, ops
-    g = torch.Generator().manual_seed(5)
-    x = _round_to(torch.randn(2, 256, 8, 256, generator=g), "bf16").cuda()
-    w = _round_to(torch.randn(256, 256, 3, 3, generator=g) / 48.0, "bf16").cuda()
-    gm, bt = (1 + 0.1 * torch.randn(256, generator=g)).cuda(), (0.1 * torch.randn(256, generator=g)).cuda()
-    y_pair = ops.gn_conv2d(x, w, None, gamma=gm, beta=bt, dtype="bf16")
-    _lib.check(_lib.lib().r2dm_set_option(b"pair", 0), "set_option")
-    y_single = ops.gn_conv2d(x, w, None, gamma=gm, beta=bt, dtype="bf16")
-    torch.cuda.synchronize()
-    assert rel_l2(y_pair, y_single) < 2e-3

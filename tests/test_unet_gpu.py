@@ -40,26 +40,6 @@ def test_forward_matches_reference_golden(golden, tag, precision):
     assert e <= TOL[precision], f"{tag}/{precision}: l2-rel {e:.3e}"
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-def test_forward_with_cta_pair_kernel(golden, mode):
-    """Config H with the eligible 3x3 convolutions on the CTA-pair kernels (opt-in; mode 1 = 256-channel
-    pairs, mode 2 = 128-channel pairs)."""
-    from r2dm_b200 import _lib
-    _lib.check(_lib.lib().r2dm_set_option(b"pair", mode), "set_option")
-    try:
-        gd = golden["H"]
-        sd = O.random_state_dict(H_CFG, gd["seed_weights"])
-        ddpm = make_ddpm(H_CFG, sd, precision="bf16")
-        g = torch.Generator().manual_seed(gd["seed_x"])
-        x = torch.randn(1, H_CFG.in_channels, *H_CFG.resolution, generator=g)
-        y = ddpm.model(x.cuda(), gd["cond"].cuda())
-        torch.cuda.synchronize()
-    finally:
-        _lib.check(_lib.lib().r2dm_set_option(b"pair", 0), "set_option")
-    e = rel_l2(y, gd["y"])
-    assert e <= TOL["bf16"], f"H/bf16/pair: l2-rel {e:.3e}"
-
-
 @pytest.mark.parametrize("enc", ["spherical_harmonics", "polar_coordinates", None])
 def test_forward_other_coordinate_encodings(enc):
     """efficient_unet.py:221-229: the spherical-harmonics (25 ch), polar (2 ch) and no encoding variants of
