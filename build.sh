@@ -3,14 +3,15 @@
 set -e
 cd "$(dirname "$0")"
 SRC=r2dm_b200/csrc
-OUT=r2dm_b200/libr2dm_b200.so
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr"
-mkdir -p build/obj
+OUT=${OUT:-r2dm_b200/libr2dm_b200.so}   # developer A/B builds: OUT=... EXTRA_FLAGS="-D..." OBJ=build/alt ./build.sh
+OBJ=${OBJ:-build/obj}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr $EXTRA_FLAGS"
+mkdir -p $OBJ
 pids=()
 for f in conv_umma elementwise attention attention_umma model; do
-  nvcc $FLAGS ${PTXAS_V:+-Xptxas -v} -c $SRC/$f.cu -o build/obj/$f.o &
+  nvcc $FLAGS ${PTXAS_V:+-Xptxas -v} -c $SRC/$f.cu -o $OBJ/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -o $OUT build/obj/conv_umma.o build/obj/elementwise.o build/obj/attention.o build/obj/attention_umma.o build/obj/model.o -cudart static
+nvcc -shared -o $OUT $OBJ/conv_umma.o $OBJ/elementwise.o $OBJ/attention.o $OBJ/attention_umma.o $OBJ/model.o -cudart static
 echo "built $OUT"

@@ -86,6 +86,12 @@ int r2dm_num_launches(r2dm_handle h); /* kernels enqueued by one r2dm_unet_forwa
 int r2dm_profile_forward(r2dm_handle h, const float* x, const float* film, float* pred, void* stream,
                          int cap, int* kind, float* ms, double* flops, double* bytes);
 
+/* Measurement aid (bench.py): enqueue only the launches of one forward whose kind bit is set (bit k = kind k
+ * above), in program order, on the buffers of the last real forward - e.g. the 56 3x3 convolutions back to
+ * back inside a CUDA graph, exactly as the product launches them.  Results are meaningless. */
+int r2dm_debug_forward_kinds(r2dm_handle h, const float* x, const float* film, float* pred,
+                             unsigned kind_mask, void* stream);
+
 /* --- sampler step arithmetic (models/diffusion/continuous_time.py:208-229, 296-299;
  *     discrete_time.py:140-179).  coef rows: {ux, up, kx, k0, kn [, qa, qs]}:
  *       x0  = clamp(ux*x + up*pred, +-clip)        (clip <= 0 disables)
@@ -169,6 +175,9 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
  * (see INTEGRATION.md "Options"); unknown names return an error. */
 int r2dm_set_option(const char* name, int value);
 int r2dm_debug_set_trace(void* buf, int cap);
+/* developer aid: every convolution launch of the forward records (first CTA start, last CTA end) in
+ * globaltimer ns into buf[launch index][2] (device uint64; works inside CUDA graphs); NULL disables. */
+int r2dm_debug_set_ktime(r2dm_handle h, void* buf);
 int r2dm_debug_tensor(r2dm_handle h, const char* name, float* out, int* C, int* H, int* W, void* stream);
 
 #ifdef __cplusplus

@@ -272,7 +272,7 @@ def conv1x1(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
 
 def resample_down2(x: Tensor) -> Tensor:
     """models/ops.py:52-146 with down=2: y[i,j] = sum_ab w_a w_b x[2i-1+a, 2j-1+b], w=[1,3,3,1]/8."""
-    w = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=x.dtype, device=x.device) / 8
+    w = (0.125, 0.375, 0.375, 0.125)     # exact in binary; Python scalars keep the function CUDA-graph capturable
     xp = ring_pad(x, 1)
     H, W = x.shape[-2:]
     y = 0

@@ -9,11 +9,12 @@ from .diffusion import (ContinuousTimeGaussianDiffusion, DiscreteTimeGaussianDif
                         GaussianDiffusion)
 from .inference import build_model, setup_model, setup_rng  # noqa: F401
 from .lidar import LiDARUtility, get_hdl64e_linear_ray_angles  # noqa: F401
+from .synthetic import randomize_, synthetic_model  # noqa: F401
 from .unet import EfficientUNet  # noqa: F401
 
 __all__ = [
     "Config", "DataConfig", "DiffusionConfig", "ModelConfig", "TrainingConfig",
     "GaussianDiffusion", "ContinuousTimeGaussianDiffusion", "DiscreteTimeGaussianDiffusion",
     "EfficientUNet", "LiDARUtility", "get_hdl64e_linear_ray_angles",
-    "build_model", "setup_model", "setup_rng",
+    "build_model", "setup_model", "setup_rng", "randomize_", "synthetic_model",
 ]

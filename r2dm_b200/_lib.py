@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libr2dm_b200.so")
+# R2DM_LIB_PATH: developer knob for A/B builds of the same C ABI (tools/); the product uses the in-tree .so
+LIB_PATH = os.environ.get("R2DM_LIB_PATH") or os.path.join(_HERE, "libr2dm_b200.so")
 
 F32, BF16 = 0, 1
 
@@ -67,6 +68,7 @@ _SIGS = {
     "r2dm_num_launches": (C.c_int, [_P]),
     "r2dm_profile_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float),
                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "r2dm_debug_forward_kinds": (C.c_int, [_P, _P, _P, _P, C.c_uint, _P]),
     "r2dm_sampler_update": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_float,
                                       _P, _P, _P, C.c_int, C.c_size_t, _P]),
     "r2dm_axpby": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_size_t, _P]),
@@ -92,6 +94,7 @@ _SIGS = {
                                     C.c_size_t, _P]),
     "r2dm_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "r2dm_debug_set_trace": (C.c_int, [_P, C.c_int]),
+    "r2dm_debug_set_ktime": (C.c_int, [_P, _P]),
     "r2dm_debug_tensor": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), _P]),
 }

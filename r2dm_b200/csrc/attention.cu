@@ -24,6 +24,8 @@ attention_kernel(const uint4* __restrict__ qkv, uint4* __restrict__ out, int E, 
   const int tok = qt * 128 + threadIdx.x;
   const int qy = tok / W, qx = tok % W;
   const float qscale = rsqrtf(static_cast<float>(HD)) * 1.4426950408889634f;
+  pdl_launch_dependents();
+  pdl_wait();
 
   float q[HD], acc[HD];
 #pragma unroll
@@ -105,15 +107,13 @@ cudaError_t attention_launch(int dtype, PT qkv, PT out, int heads, cudaStream_t 
   const uint4* in = static_cast<const uint4*>(qkv.ptr);
   uint4* o = static_cast<uint4*>(out.ptr);
   if (dtype == kBF16) {
-    if (hd == 64) attention_kernel<__nv_bfloat16, 64><<<grid, 128, 0, s>>>(in, o, E, out.H, out.W, heads);
-    else if (hd == 32) attention_kernel<__nv_bfloat16, 32><<<grid, 128, 0, s>>>(in, o, E, out.H, out.W, heads);
-    else return cudaErrorInvalidConfiguration;
+    if (hd == 64) return launch_pdl(attention_kernel<__nv_bfloat16, 64>, grid, dim3(128), 0, s, in, o, E, out.H, out.W, heads);
+    if (hd == 32) return launch_pdl(attention_kernel<__nv_bfloat16, 32>, grid, dim3(128), 0, s, in, o, E, out.H, out.W, heads);
   } else {
-    if (hd == 64) attention_kernel<float, 64><<<grid, 128, 0, s>>>(in, o, E, out.H, out.W, heads);
-    else if (hd == 32) attention_kernel<float, 32><<<grid, 128, 0, s>>>(in, o, E, out.H, out.W, heads);
-    else return cudaErrorInvalidConfiguration;
+    if (hd == 64) return launch_pdl(attention_kernel<float, 64>, grid, dim3(128), 0, s, in, o, E, out.H, out.W, heads);
+    if (hd == 32) return launch_pdl(attention_kernel<float, 32>, grid, dim3(128), 0, s, in, o, E, out.H, out.W, heads);
   }
-  return cudaGetLastError();
+  return cudaErrorInvalidConfiguration;
 }
 
 }  // namespace r2dm

@@ -60,6 +60,10 @@ __global__ void __launch_bounds__(128, 2) attention_umma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_S = tmem_slot, tmem_O = tmem_slot + 128;
+  // programmatic dependent launch: the set-up above overlapped the tail of the in-projection; nothing
+  // produced by it is read before this point, and the out-projection may start its own set-up now
+  pdl_launch_dependents();
+  pdl_wait();
 
   auto load_kv = [&](int j, int st) {
     const int ky = (j * 128) / p.W, kx0 = (j * 128) % p.W;
@@ -204,8 +208,7 @@ static cudaError_t launch_attn(const PT& qkv, const PT& out, int heads, const CU
   if (swap < 0) { const char* e = getenv("R2DM_ATTN_MNSWAP"); swap = e ? atoi(e) : 0; }
   p.mn_swap = swap;
   dim3 grid(out.H * out.W / 128, heads, out.B);
-  kern<<<grid, 128, SMEM, s>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(kern, grid, dim3(128), SMEM, s, p);
 }
 
 cudaError_t attention_umma_launch(PT qkv, PT out, int heads, const CUtensorMap& tm, cudaStream_t s) {

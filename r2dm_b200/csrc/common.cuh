@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace r2dm {
 
@@ -37,6 +38,16 @@ struct Elem<float> {
     for (int i = 0; i < 4; ++i) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r[i]) : "f"(v[i]));
     return make_uint4(r[0], r[1], r[2], r[3]);
   }
+  // packed-pair views (CW / 2 pairs per 16-byte unit)
+  __device__ static __forceinline__ void unpack2x(const uint4& u, f32x2* v) {
+    v[0] = pack2(__uint_as_float(u.x), __uint_as_float(u.y));
+    v[1] = pack2(__uint_as_float(u.z), __uint_as_float(u.w));
+  }
+  __device__ static __forceinline__ uint4 pack2x(const f32x2* v) {
+    float a, b, c, d;
+    unpack2(v[0], a, b); unpack2(v[1], c, d);
+    return make_uint4(__float_as_uint(a), __float_as_uint(b), __float_as_uint(c), __float_as_uint(d));
+  }
 };
 template <>
 struct Elem<__nv_bfloat16> {
@@ -60,6 +71,23 @@ struct Elem<__nv_bfloat16> {
     return make_uint4(w[0], w[1], w[2], w[3]);
   }
   __device__ static __forceinline__ uint4 pack_mma(const float* v) { return pack(v); }
+  // packed-pair views (CW / 2 pairs per 16-byte unit): word i holds channels (2i, 2i+1)
+  __device__ static __forceinline__ void unpack2x(const uint4& u, f32x2* v) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = pack2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+  }
+  __device__ static __forceinline__ uint4 pack2x(const f32x2* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float lo, hi;
+      unpack2(v[i], lo, hi);
+      __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+      w[i] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
 };
 
 // index (in 16-byte units) of pixel (y, xp) of plane `pl` of image b

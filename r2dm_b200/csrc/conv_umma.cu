@@ -73,6 +73,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __shared__ __align__(16) float bias_s[NT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.ktime != nullptr && threadIdx.x == 0) atomicMin(p.ktime, gtime());
   const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * p.tiles_total / gridDim.x);
   const int t_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.tiles_total / gridDim.x);
   const uint32_t wres_bytes = p.wres ? static_cast<uint32_t>(p.nk) * Tr::B_BYTES : 0u;
@@ -91,7 +92,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     tma_prefetch_desc(&p.tmap0);
     if (p.ksplit < p.nk) tma_prefetch_desc(&p.tmap1);
   }
-  if (warp == 2) tmem_alloc<Tr::TMEM_COLS>(&tmem_slot);
+  if (warp == kAllocWarp) tmem_alloc<Tr::TMEM_COLS>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -115,7 +116,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     b = t / p.ytiles;
   };
 
-  if (warp == 0) {
+  if (warp == kProdWarp) {
     // ------------------------------------------------------------------ producer
     if (lane == 0) {
       if (p.wres) {
@@ -150,7 +151,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     // the whole warp runs this loop convergently; one elected lane issues (see umma_f16_warp)
     {
@@ -251,7 +252,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         umma_commit_warp(&acc_full[buf]);
       }
     }
-  } else if (warp >= 4 && warp < kEpiWarp0) {
+  } else if (warp >= kXfWarp0 && warp < kXfWarp0 + 8) {
     // ------------------------------------------------------------------ operand transform
     // Two groups of four warps; group g transforms the pipeline stages with (global index % 2) == g,
     // so two stages are in flight and the XU (tanh) pipe of every SM sub-partition always has a
@@ -259,8 +260,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     if (p.xf.enabled) {
       const double inv_cnt = 1.0 / (static_cast<double>((p.xf.C0 + p.xf.C1) / p.xf.groups) * p.H * p.W);
       pdl_wait();
-      const int grp = (warp - 4) >> 2;                  // 0 / 1
-      const int t256 = threadIdx.x - 128;               // 0..255 over both groups
+      const int grp = (warp - kXfWarp0) >> 2;           // 0 / 1
+      const int t256 = threadIdx.x - kXfWarp0 * 32;     // 0..255 over both groups
       const int tt = t256 & 127;                        // 0..127 within the group
       constexpr int TPP = 128 / Tr::PLANES;             // threads per channel plane
       const int my_plane = tt / TPP, tip = tt % TPP;
@@ -358,26 +359,47 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         const int n_units = (row_hi - row_lo) * Tr::APITCH;
         for (int ks = 0; ks < p.nk; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
           if ((it & 1u) != static_cast<uint32_t>(grp)) continue;
-          float ca[CW], cd[CW];
+          // per-channel coefficients of this thread's plane as fp32 pairs (channels 2i, 2i+1)
+          f32x2 ca2[CW / 2], cd2[CW / 2];
           const int c0 = (ks * Tr::PLANES + my_plane) * CW;
 #pragma unroll
-          for (int i = 0; i < CW; ++i) {
-            const bool ok = c0 + i < Ctot;
-            ca[i] = ok ? coef_a[c0 + i] : 0.f;
-            cd[i] = ok ? coef_d[c0 + i] : 0.f;
+          for (int i = 0; i < CW / 2; ++i) {
+            const bool ok = c0 + 2 * i < Ctot;     // Ctot is a multiple of CW: a plane is all real or all padding
+            const float2 a = ok ? *reinterpret_cast<const float2*>(coef_a + c0 + 2 * i) : make_float2(0.f, 0.f);
+            const float2 d = ok ? *reinterpret_cast<const float2*>(coef_d + c0 + 2 * i) : make_float2(0.f, 0.f);
+            ca2[i] = pack2(a.x, a.y);
+            cd2[i] = pack2(d.x, d.y);
           }
           mbar_wait_relaxed(&full_bar[st], ph, 500);
           if (tt == 0) R2DM_TRACE(grp ? 4 : 2, 2 * it);
           const uint32_t sbase = smem_u32(smem_ring + static_cast<size_t>(st) * p.stage_bytes +
                                           my_plane * Tr::A_PLANE_BYTES) + row_lo * Tr::APITCH * 16;
+          // y = silu(a x + d): packed fp32 FMAs (one issue slot per two channels), one MUFU.TANH per channel
           auto xform_unit = [&](uint4 raw) {
-            float v[CW];
-            Elem<T>::unpack(raw, v);
+            f32x2 v2[CW / 2];
+            Elem<T>::unpack2x(raw, v2);
 #pragma unroll
-            for (int k = 0; k < CW; ++k) {
-              const float tv = fmaf(v[k], ca[k], cd[k]);
-              v[k] = p.xf.silu ? (sizeof(T) == 2 ? silu_from_half(tv) : silu_f(tv)) : tv;
+            for (int k = 0; k < CW / 2; ++k) {
+              const f32x2 t2 = fma2(v2[k], ca2[k], cd2[k]);
+              if (p.xf.silu) {
+                float lo, hi;
+                unpack2(t2, lo, hi);
+                if (sizeof(T) == 2) {
+                  float tl, th;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(tl) : "f"(lo));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
+                  v2[k] = fma2(t2, pack2(tl, th), t2);      // h + h tanh(h), h = t / 2 (folded into a, d)
+                } else {
+                  v2[k] = pack2(silu_f(lo), silu_f(hi));
+                }
+              } else {
+                v2[k] = t2;
+              }
             }
+            if (sizeof(T) == 2) return Elem<T>::pack2x(v2);
+            float v[CW];
+#pragma unroll
+            for (int k = 0; k < CW / 2; ++k) unpack2(v2[k], v[2 * k], v[2 * k + 1]);
             return Elem<T>::pack_mma(v);
           };
           if (c0 < Ctot && p.xf.debug == 0) {
@@ -404,7 +426,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         }
       }
     }
-  } else if (warp >= kEpiWarp0) {
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 8) {
     // ------------------------------------------------------------------ epilogue
     // Compact on purpose: the column-chunk loop is NOT unrolled (the fully unrolled version was
     // 96 KB of SASS and the eight epilogue warps stalled on instruction fetch).
@@ -457,9 +479,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll 1
       for (int ch = 0; ch < ((p.debug & 1) ? 0 : NCHUNK); ++ch) {
         const int c0 = c_begin + ch * CB;
-        float ssum[NSUB][2];
+        // partial (sum, sum of squares) of this warp's pixels per 8-channel sub-chunk, as fp32 pairs over
+        // (even, odd) channels: packed FADD2 / FFMA2, one issue slot per two values
+        f32x2 s1p[NSUB], s2p[NSUB];
 #pragma unroll
-        for (int u = 0; u < NSUB; ++u) { ssum[u][0] = 0.f; ssum[u][1] = 0.f; }
+        for (int u = 0; u < NSUB; ++u) { s1p[u] = pack2(0.f, 0.f); s2p[u] = pack2(0.f, 0.f); }
+        const f32x2 scale2 = pack2(p.scale, p.scale);
 #pragma unroll
         for (int r = r_begin; r < HT; r += RSTEP) {
           const int y = y0 + r;
@@ -476,37 +501,42 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             for (int h16 = 0; h16 < CB / 16; ++h16) tmem_ld16(tbase + r * NT + c0 + h16 * 16, v + h16 * 16);
             tmem_ld_wait();
             const float4* bias4 = reinterpret_cast<const float4*>(bias_s + c0);
+            f32x2 v2[CB / 2];
 #pragma unroll
             for (int i4 = 0; i4 < CB / 4; ++i4) {
               const float4 bv = bias4[i4];      // (acc + bias) * scale = acc * scale + bias * scale
-              v[4 * i4] = fmaf(v[4 * i4], p.scale, bv.x); v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], p.scale, bv.y);
-              v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], p.scale, bv.z); v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], p.scale, bv.w);
+              v2[2 * i4] = fma2(pack2(v[4 * i4], v[4 * i4 + 1]), scale2, pack2(bv.x, bv.y));
+              v2[2 * i4 + 1] = fma2(pack2(v[4 * i4 + 2], v[4 * i4 + 3]), scale2, pack2(bv.z, bv.w));
             }
             if constexpr (NCHW) {
               float* dst = p.out_nchw + ((static_cast<size_t>(b) * p.cout + n0 + c0) * p.H + y) * p.W + x;
               const size_t cstride = static_cast<size_t>(p.H) * p.W;
 #pragma unroll
-              for (int i = 0; i < CB; ++i)
-                if (n0 + c0 + i < p.cout) dst[i * cstride] = v[i];
+              for (int i = 0; i < CB / 2; ++i) {
+                float lo, hi;
+                unpack2(v2[i], lo, hi);
+                if (n0 + c0 + 2 * i < p.cout) dst[(2 * i) * cstride] = lo;
+                if (n0 + c0 + 2 * i + 1 < p.cout) dst[(2 * i + 1) * cstride] = hi;
+              }
             } else {
+              constexpr int PPU = CW / 2;                   // pairs per 16-byte unit
 #pragma unroll
               for (int u = 0; u < CB / CW; ++u) {
                 const size_t idx = idx0 + u * plane_stride;
-                float o[CW];
-#pragma unroll
-                for (int i = 0; i < CW; ++i) o[i] = v[u * CW + i];
+                f32x2* o2 = v2 + u * PPU;
                 if (res != nullptr) {
-                  float rv[CW];
-                  Elem<T>::unpack(rr[u], rv);
+                  f32x2 r2[PPU];
+                  Elem<T>::unpack2x(rr[u], r2);
 #pragma unroll
-                  for (int i = 0; i < CW; ++i) o[i] = fmaf(rv[i], p.scale, o[i]);
+                  for (int i = 0; i < PPU; ++i) o2[i] = fma2(r2[i], scale2, o2[i]);
                 }
-                float s1 = 0.f, s2 = 0.f;
+                const int sub = (u * CW) / 8;
 #pragma unroll
-                for (int i = 0; i < CW; ++i) { s1 += o[i]; s2 = fmaf(o[i], o[i], s2); }
-                ssum[(u * CW) / 8][0] += s1;
-                ssum[(u * CW) / 8][1] += s2;
-                const uint4 pk = Elem<T>::pack(o);
+                for (int i = 0; i < PPU; ++i) {
+                  s1p[sub] = add2(s1p[sub], o2[i]);
+                  s2p[sub] = fma2(o2[i], o2[i], s2p[sub]);
+                }
+                const uint4 pk = Elem<T>::pack2x(o2);
                 out[idx] = pk;
                 if (edge_warp) {                              // warp-uniform: only the two warps at the seam
                   if (x == 0) out[idx + p.W] = pk;            // xp = W+1 mirrors pixel 0
@@ -515,6 +545,13 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               }
             }
           }
+        }
+        float ssum[NSUB][2];
+#pragma unroll
+        for (int u = 0; u < NSUB; ++u) {
+          float lo, hi;
+          unpack2(s1p[u], lo, hi); ssum[u][0] = lo + hi;
+          unpack2(s2p[u], lo, hi); ssum[u][1] = lo + hi;
         }
         if (!NCHW && p.stats != nullptr) {
           // warp totals of the 2*NSUB partial sums with a transposing butterfly (NSUB*2 - 1 + 2
@@ -578,7 +615,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     p.trace[p.trace_cap - 2] = static_cast<unsigned long long>(clock64());   // ... and at the end: SM clock rate
     p.trace[p.trace_cap - 1] = gtime();
   }
-  if (warp == 2) tmem_dealloc<Tr::TMEM_COLS>(tmem);
+  if (warp == kAllocWarp) tmem_dealloc<Tr::TMEM_COLS>(tmem);
+  if (p.ktime != nullptr && threadIdx.x == 0) atomicMax(p.ktime + 1, gtime());
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -654,6 +692,12 @@ int conv_num_sms() {
   return v;
 }
 
+bool pdl_enabled() {
+  static int pdl = -1;
+  if (pdl < 0) { const char* e = getenv("R2DM_PDL"); pdl = e ? atoi(e) : 1; }
+  return pdl != 0;
+}
+
 static unsigned long long* g_trace = nullptr;
 static int g_trace_cap = 0;
 static int g_trace_skip = 0;      // developer: trace only the (skip+1)-th conv launch after conv_set_trace
@@ -723,9 +767,11 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.coef_ch = l.xf.enabled ? (p.xf.C0 + p.xf.C1 + 31) / 32 * 32 : 0;
   p.coef_bytes = 2 * p.coef_ch * static_cast<int>(sizeof(float));
   p.reverse = l.reverse;
+  p.ktime = l.ktime;
   const int avail = kSmemBudget - 256 - p.coef_bytes - (p.wres ? static_cast<int>(wbytes) : 0);
   int stages = avail / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  { const int cap = get_option("max_stages", kMaxStages); if (stages > cap) stages = cap; }
   if (stages < 2) return cudaErrorInvalidConfiguration;
   p.stages = stages;
   const int smem = 256 + p.coef_bytes + (p.wres ? static_cast<int>(wbytes) : 0) + stages * p.stage_bytes;
@@ -743,14 +789,12 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
     if (cap > 0 && grid > cap) grid = cap;
   }
   if (grid > p.tiles_total) grid = p.tiles_total;
-  static int pdl = -1;
-  if (pdl < 0) { const char* e = getenv("R2DM_PDL"); pdl = e ? atoi(e) : 1; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 

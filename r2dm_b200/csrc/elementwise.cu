@@ -80,6 +80,8 @@ cudaError_t unpack_nchw(int dtype, PT src, float* dst, int c_off, int Cdst, cuda
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ xin, int Cx, const float* __restrict__ enc, int Ce,
                                   uint4* __restrict__ dst, int planes, int H, int W, int plane_begin) {
+  pdl_launch_dependents();   // PDL: let the next kernel become resident; wait for the previous one's results
+  pdl_wait();
   constexpr int CW = Elem<T>::CW;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y % H, pl = plane_begin + blockIdx.y / H;
@@ -106,12 +108,10 @@ cudaError_t pack_input(int dtype, const float* x, int Cx, const float* enc, int 
   const int cw = dtype_cw(dtype);
   dim3 grid((dst.W + 127) / 128, dst.H * (plane_end - plane_begin), dst.B);
   if (dtype == kBF16)
-    pack_input_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(x, Cx, enc, Ce, static_cast<uint4*>(dst.ptr), dst.C / cw,
-                                                          dst.H, dst.W, plane_begin);
-  else
-    pack_input_kernel<float><<<grid, 128, 0, s>>>(x, Cx, enc, Ce, static_cast<uint4*>(dst.ptr), dst.C / cw, dst.H,
-                                                  dst.W, plane_begin);
-  return cudaGetLastError();
+    return launch_pdl(pack_input_kernel<__nv_bfloat16>, grid, dim3(128), 0, s, x, Cx, enc, Ce, static_cast<uint4*>(dst.ptr),
+                      dst.C / cw, dst.H, dst.W, plane_begin);
+  return launch_pdl(pack_input_kernel<float>, grid, dim3(128), 0, s, x, Cx, enc, Ce, static_cast<uint4*>(dst.ptr),
+                    dst.C / cw, dst.H, dst.W, plane_begin);
 }
 
 // =============================================================================== statistics
@@ -301,6 +301,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) down2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int planes,
                                                     int Hi, int Wi, float* __restrict__ stats, int slots,
                                                     int planes_per_unit) {
+  pdl_launch_dependents();   // PDL: let the next kernel become resident; wait for the previous one's results
+  pdl_wait();
   constexpr int CW = Elem<T>::CW;
   const int Ho = Hi / 2, Wo = Wi / 2;
   const int xsegs = Wo / 128;
@@ -359,18 +361,18 @@ cudaError_t down2_launch(int dtype, PT src, PT dst, cudaStream_t s) {
   dim3 grid(dst.H * (dst.W / 128), dst.C / cw, dst.B);
   const int ppu = dst.C / kNU / cw;
   if (dtype == kBF16)
-    down2_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(static_cast<const uint4*>(src.ptr), static_cast<uint4*>(dst.ptr),
-                                                     dst.C / cw, src.H, src.W, dst.stats, dst.slots, ppu);
-  else
-    down2_kernel<float><<<grid, 128, 0, s>>>(static_cast<const uint4*>(src.ptr), static_cast<uint4*>(dst.ptr),
-                                             dst.C / cw, src.H, src.W, dst.stats, dst.slots, ppu);
-  return cudaGetLastError();
+    return launch_pdl(down2_kernel<__nv_bfloat16>, grid, dim3(128), 0, s, static_cast<const uint4*>(src.ptr),
+                      static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W, dst.stats, dst.slots, ppu);
+  return launch_pdl(down2_kernel<float>, grid, dim3(128), 0, s, static_cast<const uint4*>(src.ptr),
+                    static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W, dst.stats, dst.slots, ppu);
 }
 
 // ops.Resample(up=2) in closed form (separable): y[2i] = (x[i-1] + 3x[i])/4, y[2i+1] = (3x[i] + x[i+1])/4.
 template <typename T>
 __global__ void __launch_bounds__(128) up2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int planes,
                                                   int Hi, int Wi) {
+  pdl_launch_dependents();   // PDL: let the next kernel become resident; wait for the previous one's results
+  pdl_wait();
   constexpr int CW = Elem<T>::CW;
   const int Ho = Hi * 2, Wo = Wi * 2;
   const int xsegs = Wo / 128;
@@ -409,12 +411,10 @@ cudaError_t up2_launch(int dtype, PT src, PT dst, cudaStream_t s) {
   if (dst.W % 128 != 0) return cudaErrorInvalidValue;
   dim3 grid(dst.H * (dst.W / 128), dst.C / cw, dst.B);
   if (dtype == kBF16)
-    up2_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(static_cast<const uint4*>(src.ptr), static_cast<uint4*>(dst.ptr),
-                                                   dst.C / cw, src.H, src.W);
-  else
-    up2_kernel<float><<<grid, 128, 0, s>>>(static_cast<const uint4*>(src.ptr), static_cast<uint4*>(dst.ptr),
-                                           dst.C / cw, src.H, src.W);
-  return cudaGetLastError();
+    return launch_pdl(up2_kernel<__nv_bfloat16>, grid, dim3(128), 0, s, static_cast<const uint4*>(src.ptr),
+                      static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W);
+  return launch_pdl(up2_kernel<float>, grid, dim3(128), 0, s, static_cast<const uint4*>(src.ptr),
+                    static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W);
 }
 
 // =============================================================================== conditioning
@@ -510,6 +510,8 @@ __device__ __forceinline__ float philox_normal_at(unsigned long long seed, unsig
 }
 
 __global__ void __launch_bounds__(256) sampler_update_kernel(const SamplerUpdate u) {
+  pdl_launch_dependents();   // PDL: let the next kernel become resident; wait for the previous one's results
+  pdl_wait();
   const int b = blockIdx.y;
   const int row = (u.step_ptr ? *u.step_ptr : 0) * u.rows_per_step + b * u.row_batch_stride;
   const float* cf = u.coef + static_cast<size_t>(row) * u.coef_cols;
@@ -574,8 +576,7 @@ cudaError_t sampler_update_launch(const SamplerUpdate& u, cudaStream_t s) {
   int gx = static_cast<int>((n4 + 255) / 256);
   if (gx > 148 * 4) gx = 148 * 4;
   dim3 grid(gx, u.B);
-  sampler_update_kernel<<<grid, 256, 0, s>>>(u);
-  return cudaGetLastError();
+  return launch_pdl(sampler_update_kernel, grid, dim3(256), 0, s, u);
 }
 
 __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x, const float* __restrict__ noise,
@@ -583,6 +584,8 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ x,
                                                     size_t per_sample, const int* __restrict__ step_ptr,
                                                     int rows_per_step, int row_batch_stride, const PhiloxDraw ph,
                                                     int draw) {
+  pdl_launch_dependents();   // PDL: let the next kernel become resident; wait for the previous one's results
+  pdl_wait();
   const int b = blockIdx.y;
   const int row = (step_ptr ? *step_ptr : 0) * rows_per_step + b * row_batch_stride;
   const float a = ac[2 * row], c = ac[2 * row + 1];
@@ -612,9 +615,8 @@ cudaError_t axpby_launch(const float* x, const float* noise, const float* ac, fl
   if (gx > 148 * 4) gx = 148 * 4;
   PhiloxDraw none;
   memset(&none, 0, sizeof(none));
-  axpby_kernel<<<dim3(gx, B), 256, 0, s>>>(x, noise, ac, y, per_sample, step_ptr, rows_per_step, row_batch_stride,
-                                           ph ? *ph : none, draw);
-  return cudaGetLastError();
+  return launch_pdl(axpby_kernel, dim3(gx, B), dim3(256), 0, s, x, noise, ac, y, per_sample, step_ptr, rows_per_step,
+                    row_batch_stride, ph ? *ph : none, draw);
 }
 
 __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ out, const PhiloxDraw ph, int draw,
@@ -634,10 +636,13 @@ cudaError_t philox_normal_launch(float* out, const PhiloxDraw& ph, int draw, int
   return cudaGetLastError();
 }
 
-__global__ void advance_step_kernel(int* p, int d) { *p += d; }
+__global__ void advance_step_kernel(int* p, int d) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *p += d;
+}
 cudaError_t advance_step_launch(int* step_ptr, int delta, cudaStream_t s) {
-  advance_step_kernel<<<1, 1, 0, s>>>(step_ptr, delta);
-  return cudaGetLastError();
+  return launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, s, step_ptr, delta);
 }
 
 // =============================================================================== LiDAR epilogue

@@ -6,6 +6,7 @@
 
 namespace r2dm {
 
+constexpr int kMaxConvCin = 1024;  // widest convolution input (incl. channel concat) the conv kernel is built for
 constexpr int kNU = 8;  // GroupNorm statistic units per tensor (= gn_num_groups of the reference)
 
 enum DType : int { kF32 = 0, kBF16 = 1 };
@@ -61,6 +62,7 @@ struct ConvLaunch {
   float scale;        // applied after bias (+ residual)
   float* out_nchw;    // if non-null: write fp32 [B][cout][H][W] instead of `out`
   ConvXform xf;       // fused input normalisation (enabled = 0: plain convolution)
+  unsigned long long* ktime;  // developer: device [2] receiving (first CTA start, last CTA end), globaltimer ns
   int reverse;        // tile order back to front (alternated between consecutive launches, see conv_umma.cu)
   CUtensorMap tmap0, tmap1;
 };
@@ -70,6 +72,22 @@ int conv_stage_channels(int dtype, int taps);  // K per pipeline stage
 size_t conv_packed_weight_bytes(int dtype, int taps, int nt, int cin_pad, int cout_pad);
 int conv_stat_slots(const ConvLaunch& l);
 cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s);
+// Launch with programmatic dependent launch (PDL) allowed: the kernel may become resident while its stream
+// predecessor drains; it must execute griddepcontrol.wait (pdl_wait) before touching anything a predecessor
+// wrote or still reads.  All kernels of the sampling loop use it, so a CUDA graph of the loop has
+// programmatic edges end to end (R2DM_PDL=0 switches it off).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // process-wide developer options (r2dm_set_option / R2DM_OPT_<NAME> in the environment)
 int get_option(const char* name, int dflt);
 int set_option(const char* name, int value);

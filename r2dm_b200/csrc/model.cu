@@ -1,5 +1,6 @@
 // Host runtime + C ABI: weight arena, workspace planning and the per-forward launch program of the
 // EfficientUNet (models/efficient_unet.py:188-295) built from the kernels in this directory.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -110,7 +111,7 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
 namespace r2dm {
 // Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
 static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
-static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles"};
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages"};
 int get_option(const char* name, int dflt) {
   auto& m = option_map();
   auto it = m.find(name);
@@ -291,7 +292,7 @@ struct Builder {
     l.cin_pad = w.cin_pad; l.cout = w.cout; l.cout_pad = w.cout_pad;
     l.scale = scale;
     // consecutive convolutions walk their tiles in opposite directions (L2 reuse of the previous output)
-    l.reverse = get_option("serpentine", 1) ? (n_convs & 1) : 0;
+    l.reverse = get_option("serpentine", 0) ? (n_convs & 1) : 0;
     ++n_convs;
     int out_id = -1;
     if (!is_output) {
@@ -448,6 +449,25 @@ int validate_config(const r2dm_config& c) {
     if (hd != 32 && hd != 64) return fail(-1, "head dim %d unsupported (32 or 64)", hd);
   }
   if (c.in_channels < 1 || c.in_channels > 16) return fail(-1, "in_channels out of range");
+  // widest convolution input: the bottleneck (C4) or a concatenated up-block input (2 * C[k]); the fused
+  // GroupNorm coefficient table and the per-thread channel loop of the transform are sized for kMaxConvCin
+  int C[5] = {c.base_channels, 0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) C[i + 1] = c.base_channels * c.channel_multiplier[i];
+  int widest = C[4];
+  for (int k = 1; k <= 3; ++k) widest = std::max(widest, 2 * C[k]);
+  if (widest > kMaxConvCin)
+    return fail(-1, "convolution input of %d channels exceeds the supported maximum of %d (base_channels x multipliers too large)",
+                widest, kMaxConvCin);
+  // up-blocks 3..1 read the concat [h, skip_k] (2 * C[k] channels) and produce C[k-1]; when the two are equal
+  // the reference's ResidualBlock uses an identity skip over the CONCATENATED tensor (efficient_unet.py:87-91),
+  // which this launch program (residual = first concat half) does not implement
+  for (int k = 1; k <= 3; ++k)
+    if (2 * C[k] == C[k - 1])
+      return fail(-1, "channel_multiplier makes up-block %d's concat input as wide as its output (%d): identity skip "
+                      "over a concat is not supported", k, C[k - 1]);
+  const int T = c.temb_channels > 0 ? c.temb_channels : 4 * c.base_channels;
+  if (static_cast<size_t>(8) * T * sizeof(float) > 48 * 1024 || static_cast<size_t>(c.base_channels + T) * sizeof(float) > 48 * 1024)
+    return fail(-1, "temb_channels = %d needs more than 48 KB of shared memory in the conditioning kernels (max 1536)", T);
   return 0;
 }
 
@@ -700,6 +720,32 @@ int r2dm_unet_forward(r2dm_handle h, const float* x, const float* film, const in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (Op& op : h->prog) {
     int rc = launch_op(h, op, x, film, step_ptr, rows_per_step, row_batch_stride, pred, s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// Measurement aid (bench.py): enqueue only the launches of one forward whose kind bit is set in kind_mask
+// (bit k = kind k of r2dm_profile_forward), in program order, on the buffers of the last real forward.  Lets
+// bench.py time e.g. the 56 3x3 convolutions back to back inside a CUDA graph exactly as the product
+// launches them (programmatic dependent launch, no host gaps).  Results are meaningless; never on the product path.
+int r2dm_debug_forward_kinds(r2dm_handle h, const float* x, const float* film, float* pred, unsigned kind_mask,
+                             void* stream) {
+  if (!h || !x || !film || !pred) return fail(-1, "null argument");
+  if (!h->ws) return fail(-1, "bind a workspace first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (Op& op : h->prog) {
+    int k = 0;
+    switch (op.kind) {
+      case Op::PACK_INPUT: k = 0; break;
+      case Op::CONV: k = h->convs[op.conv_w].taps == 9 ? 1 : 2; break;
+      case Op::GN: k = 3; break;
+      case Op::DOWN: k = 4; break;
+      case Op::UP: k = 5; break;
+      case Op::ATTN: k = 6; break;
+    }
+    if (!(kind_mask >> k & 1u)) continue;
+    int rc = launch_op(h, op, x, film, nullptr, 0, 1, pred, s);
     if (rc) return rc;
   }
   return 0;
@@ -1024,6 +1070,20 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
 int r2dm_set_option(const char* name, int value) {
   if (name && set_option(name, value) == 0) return 0;
   return fail(-1, "unknown option %s", name ? name : "(null)");
+}
+
+// developer: per-launch (first CTA start, last CTA end) of every convolution of the forward, written by the
+// kernels themselves (works inside CUDA graphs): buf = device uint64 [num_launches][2], or NULL to switch off.
+// Takes effect for launches / graph captures made afterwards.
+int r2dm_debug_set_ktime(r2dm_handle h, void* buf) {
+  if (!h) return fail(-1, "null argument");
+  int i = 0;
+  for (Op& op : h->prog) {
+    if (op.kind == Op::CONV)
+      op.conv.ktime = buf ? static_cast<unsigned long long*>(buf) + 2 * i : nullptr;
+    ++i;
+  }
+  return 0;
 }
 
 int r2dm_debug_set_trace(void* buf, int cap) {

@@ -77,6 +77,31 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
                : "memory");
 }
 
+// ----------------------------------------------------------------------------- packed fp32 (sm_100)
+// fma.rn.f32x2 / add.rn.f32x2 work on two fp32 values in a 64-bit register pair.  The FMA pipe delivers
+// the same results per clock as with scalar FFMA (tools/probe_f32x2.cu: 124 vs 122 per clk per SM), but
+// one issue slot covers two values - and the conv kernel's transform and epilogue warps are bound by issue
+// slots shared with the MUFU instructions (4 tanh + 28 FFMA: 95 results/clk/SM, 4 tanh + 14 FFMA2: 125).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // programmatic dependent launch: wait until the previous kernel in the stream has completed and its
 // writes are visible / allow the next kernel to begin launching
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

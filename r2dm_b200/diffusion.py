@@ -33,6 +33,11 @@ from torch import nn
 
 from . import _lib as L
 
+# `sample_and_save.py:45` wraps `ddpm.sample` in torch.compile: the loop here already IS hand-written kernels
+# inside CUDA graphs and talks to them through ctypes, which a tracing compiler cannot see - so the public
+# entry points opt out of tracing and `torch.compile(ddpm.sample)` simply calls them.
+_no_compile = getattr(getattr(torch, "compiler", None), "disable", None) or (lambda fn: fn)
+
 try:  # progress bars are optional plumbing
     from tqdm.auto import tqdm
 except Exception:  # pragma: no cover
@@ -433,6 +438,7 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         return self.log_snr(t.detach().float().cpu())[:, 0, 0, 0]
 
     # -- forward process ---------------------------------------------------------------------------
+    @_no_compile
     def q_step_from_x_0(self, x_0, step_t, rng=None):
         """continuous_time.py:169-176: x_t = alpha x_0 + sigma eps; returns (x_t, eps)."""
         x_0 = L.f32c(x_0)
@@ -442,6 +448,7 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         with torch.cuda.device(x_0.device):
             return self._axpby(x_0, noise, ac), noise
 
+    @_no_compile
     def q_step(self, x_s, step_t, step_s, rng=None):
         """continuous_time.py:178-190: q(z_t | z_s), 0 < s < t < 1."""
         x_s = L.f32c(x_s)
@@ -455,6 +462,7 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
             return self._axpby(x_s, noise, ac)
 
     # -- reverse process ---------------------------------------------------------------------------
+    @_no_compile
     @torch.inference_mode()
     def p_step(self, x_t, step_t, step_s, rng=None, mode="ddpm", ddim_eta: float = 0.0,
                _known=None, _mask=None):
@@ -480,6 +488,7 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
             self._update(x_s, x_t, pred, noise, coef, None, 0, 1, _known, _mask, noise2)
         return x_s
 
+    @_no_compile
     @torch.inference_mode()
     def sample(self, batch_size: int, num_steps: int, progress: bool = True, rng=None,
                return_all: bool = False, mode: str = "ddpm", ddim_eta: float = 0.0):
@@ -492,6 +501,7 @@ class ContinuousTimeGaussianDiffusion(GaussianDiffusion):
         coefs = continuous_coefficients(lam[:-1], lam[1:], mode, ddim_eta, self.objective)
         return self._run_table(x, lam[:-1], coefs, rng, return_all, progress, "sampling", draw_noise=True)
 
+    @_no_compile
     @torch.inference_mode()
     def repaint(self, known, mask, num_steps: int, num_resample_steps: int = 1, jump_length: int = 1,
                 progress: bool = True, rng=None, return_all: bool = False):
@@ -679,6 +689,7 @@ class DiscreteTimeGaussianDiffusion(GaussianDiffusion):
             raise ValueError(f"invalid mode {mode}")
         return torch.stack([ux, up, kx, k0, kn], dim=1)
 
+    @_no_compile
     def q_step_from_x_0(self, x_0, steps, rng=None):
         """discrete_time.py:119-124."""
         x_0 = L.f32c(x_0)
@@ -688,6 +699,7 @@ class DiscreteTimeGaussianDiffusion(GaussianDiffusion):
         with torch.cuda.device(x_0.device):
             return self._axpby(x_0, noise, ac), noise
 
+    @_no_compile
     @torch.inference_mode()
     def p_step(self, x_t, steps, rng=None, mode="ddim", eta: float = 0.0):
         """discrete_time.py:126-180."""
@@ -704,6 +716,7 @@ class DiscreteTimeGaussianDiffusion(GaussianDiffusion):
             self._update(x_s, x_t, pred, noise, coef, None, 0, 1)
         return x_s
 
+    @_no_compile
     @torch.inference_mode()
     def sample(self, batch_size: int, num_steps: int, progress: bool = True, rng=None,
                return_all: bool = False, mode: str = "ddpm"):

@@ -53,12 +53,15 @@ def setup_model(ckpt, device="cpu", ema: bool = True, show_info: bool = True, co
     """(ddpm, lidar_utils, cfg) from a reference checkpoint (path or dict with keys `cfg`, `weights`,
     `ema_weights`, `global_step`; train.py:294-304).  `compile` is accepted for signature
     compatibility and ignored: the network already runs as hand-written kernels + CUDA graph.
-    `precision`: "fp32" (tf32 tensor cores, the reference's GPU default) or "bf16"; under
-    `torch.autocast` the bf16 path is selected automatically."""
+    `precision`: "fp32" (tf32 tensor cores, the reference's GPU default) or "bf16"; with the default,
+    a surrounding bf16 `torch.autocast` selects the bf16 engine (fp16 autocast keeps fp32, see
+    EfficientUNet._active_precision)."""
     if isinstance(ckpt, (str, Path)):
         ckpt = torch.load(ckpt, map_location="cpu")
     cfg = ckpt["cfg"] if isinstance(ckpt["cfg"], Config) else Config(**ckpt["cfg"])
     ddpm = build_model(cfg, precision)
+    if precision != "fp32":
+        ddpm.model.set_precision(precision)     # explicit choice: not overridden by autocast
     state_dict = ckpt["ema_weights"] if ema else ckpt["weights"]
     ddpm.load_state_dict(state_dict)
     ddpm.eval()

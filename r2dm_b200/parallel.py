@@ -50,6 +50,23 @@ def sample_sharded(sample_fn: Callable[[List[int]], torch.Tensor], seeds: Sequen
         world, rank = 1, 0
     local = shard_seeds(seeds, world, rank)
     counts = [len(shard_seeds(seeds, world, r)) for r in range(world)]
-    out = sample_fn(local)
-    assert out.shape[0] == len(local)
+    if len(local) > 0:
+        out = sample_fn(local)
+        assert out.shape[0] == len(local)
+    else:
+        out = None   # fewer seeds than ranks (e.g. a final partial batch): nothing to sample here
+    if world > 1 and min(counts) == 0:
+        # ranks without work still have to enter the collective with the right trailing shape / dtype:
+        # take it from the lowest rank that has a sample
+        src = next(r for r in range(world) if counts[r] > 0)
+        meta = [None]
+        if rank == src:
+            meta = [(tuple(out.shape[1:]), out.dtype)]
+        dist.broadcast_object_list(meta, src=src, group=group)
+        if out is None:
+            shape, dtype = meta[0]
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+            out = torch.empty((0,) + shape, dtype=dtype, device=dev)
+    elif out is None:
+        raise ValueError("sample_sharded needs at least one seed")
     return gather_samples(out, counts, group)

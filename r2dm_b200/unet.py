@@ -21,6 +21,10 @@ from . import _lib as L
 from . import encoding
 
 
+# ctypes calls into hand-written kernels: nothing for a tracing compiler to see (see diffusion.py)
+_no_compile = getattr(getattr(torch, "compiler", None), "disable", None) or (lambda fn: fn)
+
+
 def _n_tuple(x, N: int) -> tuple:
     if isinstance(x, Iterable):
         x = tuple(x)
@@ -79,7 +83,8 @@ class EfficientUNet(nn.Module):
         self.gn_eps = gn_eps
         self.attn_num_heads = attn_num_heads
         self.coords_encoding_type = coords_encoding
-        self.precision = precision  # "fp32" (tf32 tensor cores, the reference's GPU default) | "bf16"
+        self.precision = precision or "fp32"  # "fp32" (tf32 tensor cores, the reference's GPU default) | "bf16"
+        self._precision_explicit = False      # set_precision() pins the engine regardless of autocast
 
         H, W = self.resolution
         self.register_buffer("coords", encoding.generate_polar_coords(H, W))
@@ -179,16 +184,57 @@ class EfficientUNet(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
         self._weights_version += 1
+        # the module may have moved: drop engines (C handle + weight arena + workspace) of other devices
+        dev = str(self.coords.device)
+        for key in [k for k in self._engines if k[0] != dev]:
+            self._engines.pop(key).close()
         return out
+
+    def set_precision(self, precision: str) -> "EfficientUNet":
+        """Pin the engine ("fp32" | "bf16"); an explicit choice is not overridden by autocast."""
+        if precision not in ("fp32", "tf32", "bf16"):
+            raise ValueError(f"invalid precision: {precision}")
+        self.precision = "fp32" if precision == "tf32" else precision
+        self._precision_explicit = True
+        return self
+
+    def _param_versions(self) -> int:
+        """Sum of the parameters' in-place modification counters: detects `p.data.copy_()` / optimizer-style
+        edits that bypass load_state_dict / .to()."""
+        return sum(p._version for p in self.parameters())
 
     def mark_weights_changed(self) -> None:
         """Call after editing parameters in place so the packed device copy is rebuilt."""
         self._weights_version += 1
 
     def _active_precision(self) -> str:
-        if torch.is_autocast_enabled():  # sample_and_save.py:70 runs the sampler under autocast
+        """An explicit `precision=` always wins.  With the default ("fp32") a surrounding
+        `torch.autocast("cuda", dtype=torch.bfloat16)` selects the bf16 engine; fp16 autocast
+        (sample_and_save.py:70 with the reference's default mixed_precision="fp16") keeps the fp32 (tf32
+        tensor core) engine, whose error vs the fp32 reference (1e-3) is below the reference's own fp16
+        autocast error (3e-3) - there is no fp16 engine."""
+        if self._precision_explicit or self.precision != "fp32":
+            return self.precision
+        get = getattr(torch, "get_autocast_dtype", None)
+        ac_dtype = get("cuda") if get is not None else torch.get_autocast_gpu_dtype()
+        if torch.is_autocast_enabled() and ac_dtype == torch.bfloat16:
             return "bf16"
         return self.precision
+
+    # engines hold raw C handles and device arenas: never copy / pickle them, rebuild lazily instead
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engines"] = {}
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_engines" else copy.deepcopy(v, memo)
+        return new
 
     def engine(self, precision: Optional[str] = None) -> "UNetEngine":
         precision = precision or self._active_precision()
@@ -198,6 +244,10 @@ class EfficientUNet(nn.Module):
                               "move the module to a B200 with .to('cuda')")
         key = (str(dev), precision)
         eng = self._engines.get(key)
+        pv = self._param_versions()
+        if pv != getattr(self, "_seen_param_versions", pv):
+            self._weights_version += 1       # parameters were edited in place since the last forward
+        self._seen_param_versions = pv
         if eng is None or eng.weights_version != self._weights_version:
             if eng is not None:
                 eng.close()
@@ -212,6 +262,7 @@ class EfficientUNet(nn.Module):
         with torch.no_grad():
             return self.coords_encoding(self.coords.float())[0].contiguous()
 
+    @_no_compile
     def forward(self, images: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
         if timesteps.dim() == 0:
             timesteps = timesteps[None].repeat_interleave(images.shape[0], dim=0)
@@ -370,6 +421,15 @@ class UNetEngine:
             n = L.check(self.lib.r2dm_profile_forward(self.h, L.ptr(x), L.ptr(film), L.ptr(pred), L.stream_ptr(),
                                                       cap, kind, ms, fl, by), "r2dm_profile_forward")
         return [(self.KINDS[kind[i]], ms[i], fl[i], by[i]) for i in range(n)]
+
+    def forward_kinds(self, x: torch.Tensor, film: torch.Tensor, pred: torch.Tensor, kinds) -> None:
+        """Measurement aid: enqueue only the launches of the given kinds (names from KINDS) of one forward."""
+        mask = 0
+        for k in kinds:
+            mask |= 1 << self.KINDS.index(k)
+        self.bind(x.shape[0])
+        L.check(self.lib.r2dm_debug_forward_kinds(self.h, L.ptr(x), L.ptr(film), L.ptr(pred), mask, L.stream_ptr()),
+                "r2dm_debug_forward_kinds")
 
     def debug_tensor(self, name: str) -> torch.Tensor:
         """fp32 NCHW copy of a named intermediate of the last forward (needs R2DM_KEEP_ACTIVATIONS=1)."""

@@ -12,7 +12,7 @@ then follow their own deterministic path - this is true of the reference itself 
   (1) teacher-forced single steps anywhere along the 256-step trajectory (reference x_k in, reference
       x_{k+1} expected) at the single-forward tolerance,
   (2) the free-running trajectories at stated l2 bounds per checkpoint (measured curves are written to
-      gpurun_out/ and committed under profiles/), and
+      gpurun_out/ and committed as profiles/r02_traj_parity.json), and
   (3) distribution-level agreement of the final samples (mean / std / saturation fraction).
 Tolerances are per engine and stated in TOL below.
 """
@@ -28,10 +28,13 @@ from tests.util_model import make_ddpm
 
 pytestmark = pytest.mark.gpu
 
-# l2-relative bounds vs the fp32 CPU reference
+# l2-relative bounds vs the fp32 CPU reference.  Measured on B200 (profiles/r02_traj_parity.json):
+#   fp32 engine: ddim32 5.3e-3, ddpm256 1.0e-3, ddim256 2.0e-3, repaint 3.3e-3 (max over states), steps 2.5e-4
+#   bf16 engine: ddim32 2.0e-2, ddpm256 7.8e-3, ddim256 1.2e-2, repaint 1.1e-2,                   steps 5.1e-4
+# (the fixture stores reference outputs as fp16: a 2.4e-4 floor).  Bounds = roughly 2.5x the measurement.
 TOL = {
-    "fp32": dict(step=5e-3, traj32=6e-2, traj256=1.5e-1, repaint=6e-2),
-    "bf16": dict(step=3e-2, traj32=2.5e-1, traj256=4e-1, repaint=2.5e-1),
+    "fp32": dict(step=2e-3, traj32=1.5e-2, traj256=6e-3, repaint=1e-2),
+    "bf16": dict(step=3e-3, traj32=5e-2, traj256=3e-2, repaint=3e-2),
 }
 
 
@@ -126,9 +129,7 @@ def test_teacher_forced_steps_along_256(engine, golden, mode):
         errs[int(k)] = rel_l2(sub(y), xk1_sub)
     torch.cuda.synchronize()
     _dump(f"traj_teacher_forced_{mode}_{prec}.json", errs)
-    # step 0 divides by alpha(1) = 5.5e-4 before clipping: it gets the trajectory tolerance
-    assert errs[0] <= TOL[prec]["traj32"], errs
-    assert max(v for k, v in errs.items() if k > 0) <= TOL[prec]["step"], errs
+    assert max(errs.values()) <= TOL[prec]["step"], errs
 
 
 def test_repaint_trajectory(engine, golden):
@@ -145,6 +146,6 @@ def test_repaint_trajectory(engine, golden):
     curve = {i: rel_l2(sub(ys[i]), gd["subs"][i]) for i in range(ys.shape[0])}
     fin = _final_stats(ys[-1], gd["final"])
     _dump(f"traj_repaint_{prec}.json", dict(curve=curve, final=fin))
-    assert fin["l2_rel"] <= TOL[prec]["repaint"], fin
+    assert max(curve.values()) <= TOL[prec]["repaint"] and fin["l2_rel"] <= TOL[prec]["repaint"], (curve, fin)
     y = ys[-1].cpu()
     assert (y - known)[mask.bool()].abs().max() < 5e-3

@@ -7,6 +7,8 @@ import r2dm_b200 as R
 def make_cfg(ucfg, timestep_type="continuous", schedule="cosine", objective="eps", num_training_steps=None):
     cfg = R.Config()
     cfg.data.resolution = tuple(ucfg.resolution)
+    assert ucfg.in_channels in (1, 2)
+    cfg.data.train_reflectance = ucfg.in_channels == 2     # utils/inference.py:31-36: depth [+ reflectance]
     cfg.model.base_channels = ucfg.base_channels
     cfg.model.temb_channels = ucfg.temb_channels
     cfg.model.channel_multiplier = tuple(ucfg.channel_multiplier)
