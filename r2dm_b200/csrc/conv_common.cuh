@@ -42,9 +42,13 @@ struct XformParams {
 
 struct ConvParams {
   CUtensorMap tmap0, tmap1;
+  CUtensorMap tmap2, tmap3;   // skip stages (folded 1x1 projection): raw skip input(s)
   XformParams xf;
   const void* wpacked;
   const float* bias;
+  const void* w2packed;   // skip stages: packed 1x1 weights [nt][stage][plane][co][cw]
+  const float* bias2;     // skip projection bias (added to bias), or null
+  int nk2, ksplit2;       // number of skip stages per tile (0 = none); first one that reads tmap3
   const void* residual;
   void* out;
   float* out_nchw;

@@ -55,6 +55,18 @@ struct ConvTraits {
                                    : 2 * ACC_COLS <= 256 ? 256 : 512;
   static_assert(2 * ACC_COLS <= 512, "double-buffered accumulators exceed TMEM");
   static_assert(B_BYTES % 128 == 0, "weight stage must stay 128B aligned");
+  // Skip stages (3x3 kernels only): extra K stages of a 1x1 convolution over a second, untransformed input
+  // accumulated into the same tile - the ResidualBlock's skip projection (efficient_unet.py:87-91,108) folded into
+  // conv2.  One skip stage = SK_PLANES channel planes of the HT x 128 centre pixels + the matching weight rows;
+  // it reuses a ring slot, so it must fit in the 3x3 stage (resident 3x3 weights: the A part alone).
+  static constexpr int SK_PLANES = NT >= 128 ? 8 : 2;
+  static constexpr int SK_KCH = SK_PLANES * CW;
+  static constexpr int SK_A_PLANE_BYTES = HT * 128 * 16;
+  static constexpr int SK_A_BYTES = SK_PLANES * SK_A_PLANE_BYTES;
+  static constexpr int SK_B_PLANE_BYTES = NT * 16;
+  static constexpr int SK_B_BYTES = SK_PLANES * SK_B_PLANE_BYTES;
+  static_assert(TAPS != 9 || NT < 64 || SK_A_BYTES + SK_B_BYTES <= A_BYTES_AL + (NT >= 128 ? B_BYTES : 0),
+                "skip stage does not fit in a ring slot");
 };
 
 // silu(t) = h + h tanh(h) with h = t/2 (the 1/2 is folded into the affine coefficients): one MUFU op
@@ -91,6 +103,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     fence_mbar_init();
     tma_prefetch_desc(&p.tmap0);
     if (p.ksplit < p.nk) tma_prefetch_desc(&p.tmap1);
+    if (p.nk2 > 0) { tma_prefetch_desc(&p.tmap2); if (p.ksplit2 < p.nk2) tma_prefetch_desc(&p.tmap3); }
   }
   if (warp == kAllocWarp) tmem_alloc<Tr::TMEM_COLS>(&tmem_slot);
   tc_fence_before();
@@ -148,6 +161,19 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           if (!p.wres)
             bulk_load(sa + Tr::A_BYTES_AL, wsrc + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES, &full_bar[st]);
           R2DM_TRACE(0, it);
+        }
+        if constexpr (TAPS == 9) {
+          // skip stages: centre pixels of the raw skip input(s) + their 1x1 weight rows
+          const uint8_t* w2src = static_cast<const uint8_t*>(p.w2packed) + static_cast<size_t>(nt) * p.nk2 * Tr::SK_B_BYTES;
+          for (int ks = 0; ks < p.nk2; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
+            mbar_wait_relaxed(&empty_bar[st], ph ^ 1, 2000);
+            uint8_t* sa = smem_ring + static_cast<size_t>(st) * p.stage_bytes;
+            mbar_expect_tx(&full_bar[st], Tr::SK_A_BYTES + Tr::SK_B_BYTES);
+            const bool second = ks >= p.ksplit2;
+            const int plane0 = (second ? ks - p.ksplit2 : ks) * Tr::SK_PLANES;
+            tma_load_5d(sa, second ? &p.tmap3 : &p.tmap2, &full_bar[st], 2 * (x0 + 1), 0, y0, plane0, b);
+            bulk_load(sa + Tr::SK_A_BYTES, w2src + static_cast<size_t>(ks) * Tr::SK_B_BYTES, Tr::SK_B_BYTES, &full_bar[st]);
+          }
         }
       }
     }
@@ -248,6 +274,31 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           }
           umma_commit_warp(&empty_bar[st]);  // frees this smem stage once the MMAs above have read it
           if (lane == 0) R2DM_TRACE(1, 2 * it + 1);
+        }
+        if constexpr (TAPS == 9) {
+          // skip stages: plain 1x1 MMAs (one per output row and 16-byte K step) into the same accumulators
+          for (int ks = 0; ks < p.nk2; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
+            mbar_wait(p.xf.enabled ? &xf_bar[st] : &full_bar[st], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem_ring + static_cast<size_t>(st) * p.stage_bytes);
+            const uint32_t sb = sa + Tr::SK_A_BYTES;
+            const uint32_t a_lo0 = (static_cast<uint32_t>(Tr::SK_A_PLANE_BYTES >> 4) << 16) | ((sa >> 4) & 0x3FFFu);
+            const uint32_t b_lo0 = (static_cast<uint32_t>(Tr::SK_B_PLANE_BYTES >> 4) << 16) | ((sb >> 4) & 0x3FFFu);
+            constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
+#pragma unroll
+            for (int kk = 0; kk < Tr::SK_PLANES / 2; ++kk) {
+#pragma unroll
+              for (int r = 0; r < HT; ++r) {
+                const uint32_t a_add = static_cast<uint32_t>((kk * 2 * Tr::SK_A_PLANE_BYTES + r * 128 * 16) >> 4);
+                const uint32_t b_add = static_cast<uint32_t>((kk * 2 * Tr::SK_B_PLANE_BYTES) >> 4);
+                const uint64_t adesc = (static_cast<uint64_t>(kHi) << 32) | (a_lo0 + a_add);
+                const uint64_t bdesc = (static_cast<uint64_t>(kHi) << 32) | (b_lo0 + b_add);
+                if (Elem<T>::kFmt == 2) umma_tf32_warp(dbase + r * NT, adesc, bdesc, idesc, 1u);
+                else umma_f16_warp(dbase + r * NT, adesc, bdesc, idesc, 1u);
+              }
+            }
+            umma_commit_warp(&empty_bar[st]);
+          }
         }
         umma_commit_warp(&acc_full[buf]);
       }
@@ -424,6 +475,15 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           if (lane == 0) mbar_arrive(&xf_bar[st]);
           if (tt == 0) R2DM_TRACE(grp ? 4 : 2, 2 * it + 1);
         }
+        if constexpr (TAPS == 9) {
+          // skip stages carry raw data: nothing to transform, only forward "landed" to the MMA warp
+          for (int ks = 0; ks < p.nk2; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
+            if ((it & 1u) != static_cast<uint32_t>(grp)) continue;
+            mbar_wait_relaxed(&full_bar[st], ph, 500);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xf_bar[st]);
+          }
+        }
       }
     }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 8) {
@@ -458,7 +518,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       if (nt != cur_nt) {   // bias of this N tile -> shared memory (once per CTA when ntiles == 1)
         cur_nt = nt;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        for (int i = ethread; i < NT; i += 256) bias_s[i] = p.bias[n0 + i] * p.scale;   // pre-scaled: one FMA per value
+        for (int i = ethread; i < NT; i += 256)   // pre-scaled: one FMA per value; bias2 = the folded skip projection's
+          bias_s[i] = (p.bias[n0 + i] + (p.bias2 ? p.bias2[n0 + i] : 0.f)) * p.scale;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       if (!NCHW && res != nullptr) {
@@ -637,6 +698,7 @@ static EncodeTiledFn get_encode() {
 
 static int ks_for(int taps) { return taps == 9 ? 1 : 4; }
 int conv_stage_channels(int dtype, int taps) { return ks_for(taps) * 2 * dtype_cw(dtype); }
+int conv_skip_planes(int nt) { return nt >= 128 ? 8 : 2; }   // = ConvTraits::SK_PLANES
 
 size_t conv_packed_weight_bytes(int dtype, int taps, int nt, int cin_pad, int cout_pad) {
   (void)nt;
@@ -680,6 +742,15 @@ int conv_make_tmaps(ConvLaunch& l) {
   if (rc) return rc;
   if (l.in1.ptr) rc = make_one_tmap(&l.tmap1, l.dtype, l.in1, bw, bh, planes);
   else l.tmap1 = l.tmap0;
+  if (rc) return rc;
+  l.tmap2 = l.tmap3 = l.tmap0;
+  if (l.sk0.ptr) {
+    if (l.taps != 9) return -2;
+    rc = make_one_tmap(&l.tmap2, l.dtype, l.sk0, 128, l.ht, conv_skip_planes(l.nt));
+    if (rc) return rc;
+    if (l.sk1.ptr) rc = make_one_tmap(&l.tmap3, l.dtype, l.sk1, 128, l.ht, conv_skip_planes(l.nt));
+    else l.tmap3 = l.tmap2;
+  }
   return rc;
 }
 
@@ -729,8 +800,15 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   }
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  p.tmap0 = l.tmap0; p.tmap1 = l.tmap1;
+  p.tmap0 = l.tmap0; p.tmap1 = l.tmap1; p.tmap2 = l.tmap2; p.tmap3 = l.tmap3;
   p.wpacked = l.wpacked; p.bias = l.bias; p.residual = l.residual;
+  if (l.sk0.ptr != nullptr) {
+    if (TAPS != 9 || l.w2packed == nullptr || l.cin2_pad % Tr::SK_KCH != 0 || l.sk0.C % Tr::SK_KCH != 0)
+      return cudaErrorInvalidValue;
+    p.w2packed = l.w2packed; p.bias2 = l.bias2;
+    p.nk2 = l.cin2_pad / Tr::SK_KCH;
+    p.ksplit2 = l.sk1.ptr ? l.sk0.C / Tr::SK_KCH : p.nk2;
+  }
   p.out = l.out.ptr; p.out_nchw = l.out_nchw; p.stats = l.out_nchw ? nullptr : l.out.stats;
   p.B = l.out.B; p.H = l.out.H; p.W = l.out.W;
   p.cout = l.cout; p.cout_pad = l.cout_pad;
@@ -763,7 +841,9 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   // ring stages as the budget allows
   const size_t wbytes = static_cast<size_t>(p.nk) * Tr::B_BYTES;
   p.wres = (p.ntiles == 1 && wbytes <= static_cast<size_t>(kWresMaxBytes)) ? 1 : 0;
+  if (p.nk2 > 0 && p.wres && Tr::SK_A_BYTES + Tr::SK_B_BYTES > Tr::A_BYTES_AL) p.wres = 0;   // a skip stage must fit in a slot
   p.stage_bytes = Tr::A_BYTES_AL + (p.wres ? 0 : Tr::B_BYTES);
+  if (p.nk2 > 0 && Tr::SK_A_BYTES + Tr::SK_B_BYTES > p.stage_bytes) return cudaErrorInvalidConfiguration;
   p.coef_ch = l.xf.enabled ? (p.xf.C0 + p.xf.C1 + 31) / 32 * 32 : 0;
   p.coef_bytes = 2 * p.coef_ch * static_cast<int>(sizeof(float));
   p.reverse = l.reverse;
@@ -772,6 +852,11 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   int stages = avail / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   { const int cap = get_option("max_stages", kMaxStages); if (stages > cap) stages = cap; }
+  // The two transform groups take alternating stages.  With an ODD ring depth the owner of a slot would alternate
+  // between its uses, and a group that is ahead (e.g. after pass-through skip stages, whose small loads can land
+  // before the preceding larger one) would wait for phase k+1 of a slot whose phase k has not completed yet - an
+  // mbarrier parity wait cannot tell these apart and passes immediately.  An even depth keeps one owner per slot.
+  if (l.xf.enabled && stages > 2) stages &= ~1;
   if (stages < 2) return cudaErrorInvalidConfiguration;
   p.stages = stages;
   const int smem = 256 + p.coef_bytes + (p.wres ? static_cast<int>(wbytes) : 0) + stages * p.stage_bytes;
@@ -864,8 +949,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 }
 
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin, int cin_pad,
-                             int cout_pad, void* dst, cudaStream_t s) {
-  const int planes = 2 * ks_for(taps);
+                             int cout_pad, void* dst, cudaStream_t s, int planes_arg) {
+  const int planes = planes_arg > 0 ? planes_arg : 2 * ks_for(taps);
   const int fuse = (taps == 9 && (nt == 64 || nt == 128 || nt == 16)) ? 1 : 0;
   const size_t total = static_cast<size_t>(taps) * cin_pad * cout_pad;
   const int grid = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);

@@ -61,14 +61,21 @@ struct ConvLaunch {
   const void* residual;  // planar-16 tensor added before scaling, or null
   float scale;        // applied after bias (+ residual)
   float* out_nchw;    // if non-null: write fp32 [B][cout][H][W] instead of `out`
+  // folded skip projection (3x3 launches only): out += conv1x1(sk0 ++ sk1) + bias2, accumulated as extra K
+  // stages of the same tile from the RAW (untransformed) tensors; sk0.ptr == nullptr: none
+  PT sk0, sk1;
+  int cin2_pad;
+  const void* w2packed;   // pack_conv_weight(taps = 1, ..., planes = conv_skip_planes(nt))
+  const float* bias2;
   ConvXform xf;       // fused input normalisation (enabled = 0: plain convolution)
   unsigned long long* ktime;  // developer: device [2] receiving (first CTA start, last CTA end), globaltimer ns
   int reverse;        // tile order back to front (alternated between consecutive launches, see conv_umma.cu)
-  CUtensorMap tmap0, tmap1;
+  CUtensorMap tmap0, tmap1, tmap2, tmap3;
 };
 // Fills l.tmap0/tmap1 for the current in0/in1 pointers.  Returns 0 on success.
 int conv_make_tmaps(ConvLaunch& l);
 int conv_stage_channels(int dtype, int taps);  // K per pipeline stage
+int conv_skip_planes(int nt);                  // channel planes per skip stage of a 3x3 launch with N tile nt
 size_t conv_packed_weight_bytes(int dtype, int taps, int nt, int cin_pad, int cout_pad);
 int conv_stat_slots(const ConvLaunch& l);
 cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s);
@@ -94,8 +101,9 @@ int set_option(const char* name, int value);
 // developer timeline of CTA 0 of subsequent conv launches: buf[4 roles][cap] (globaltimer ns), or null
 void conv_set_trace(unsigned long long* buf, int cap);
 // w: fp32 [cout][cin][k][k] (OIHW), k*k == taps
+// planes: channel planes per K stage (0 = the kernel's own stage width for `taps`)
 cudaError_t pack_conv_weight(int dtype, int taps, int nt, const float* w, int cout, int cin,
-                             int cin_pad, int cout_pad, void* dst, cudaStream_t s);
+                             int cin_pad, int cout_pad, void* dst, cudaStream_t s, int planes = 0);
 
 // ------------------------------------------------------------------ layout conversion
 cudaError_t pack_nchw(int dtype, const float* src, int B, int Csrc, int H, int W, PT dst,

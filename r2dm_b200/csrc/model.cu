@@ -38,6 +38,7 @@ struct ConvW {
   int taps = 9, cin = 0, cout = 0, cin_pad = 0, cout_pad = 0, nt = 64;
   size_t w_off = 0, b_off = 0;
   bool w_ok = false, b_ok = false;
+  int sk_planes = 0;   // > 0: a skip projection folded into its block's conv2 (packed with this stage width)
 };
 struct RawW {  // fp32 tensor copied verbatim into the arena at dst_off (+ row offset for stacked)
   std::string name;
@@ -60,6 +61,7 @@ struct Op {
   PT a, b;
   int heads = 0;
   int conv_w = -1;        // index into convs (weights/bias resolved at bind)
+  int skip_w = -1;        // index of the skip projection folded into this launch, or -1
   int gn_gamma = -1;      // raw index of gamma (beta = +1), or -1 for AdaGN
   bool is_output = false; // network output conv (writes pred NCHW)
   bool xf_film = false;   // conv with fused AdaGN: film pointers patched per forward
@@ -111,7 +113,7 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
 namespace r2dm {
 // Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
 static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
-static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages"};
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip"};
 int get_option(const char* name, int dflt) {
   auto& m = option_map();
   auto it = m.find(name);
@@ -136,12 +138,13 @@ int pick_nt(int cout) {
   return cout % 128 == 0 ? 128 : 64;
 }
 
-int add_conv(r2dm_model* m, const std::string& name, int taps, int cin, int cout) {
+int add_conv(r2dm_model* m, const std::string& name, int taps, int cin, int cout, bool folded_skip = false) {
   ConvW c;
   c.name = name;
   c.taps = taps; c.cin = cin; c.cout = cout;
   c.nt = pick_nt(cout);
-  c.cin_pad = round_up(cin, conv_stage_channels(m->dtype, taps));
+  c.sk_planes = folded_skip ? conv_skip_planes(c.nt) : 0;
+  c.cin_pad = round_up(cin, folded_skip ? c.sk_planes * dtype_cw(m->dtype) : conv_stage_channels(m->dtype, taps));
   c.cout_pad = round_up(cout, c.nt);
   c.w_off = m->arena_bytes;
   m->arena_bytes += align_up(conv_packed_weight_bytes(m->dtype, taps, c.nt, c.cin_pad, c.cout_pad), 256);
@@ -186,7 +189,7 @@ int plan_weights(r2dm_model* m) {
       m->film_rows[p + ".norm2.proj.1"] = {F, 2 * b.cout};
       F += 2 * b.cout;
       add_conv(m, p + ".conv2", 9, b.cout, b.cout);
-      if (ci != b.cout) add_conv(m, p + ".skip", 1, ci, b.cout);
+      if (ci != b.cout) add_conv(m, p + ".skip", 1, ci, b.cout, get_option("fold_skip", 1) != 0);
     }
     if (b.attn) {
       const std::string p = b.name + ".self_attn_block";
@@ -265,7 +268,8 @@ struct Builder {
   // xf: 0 none, 1 GroupNorm(affine from raw index gamma_raw)+SiLU, 2 AdaGN(film_name)+SiLU,
   //     3 GroupNorm(affine) without SiLU (attention)
   int conv(const std::string& wname, int in0, int in1, int residual, float scale, bool want_stats,
-           bool is_output = false, int xf = 0, int gamma_raw = -1, const std::string& film_name = "") {
+           bool is_output = false, int xf = 0, int gamma_raw = -1, const std::string& film_name = "",
+           const std::string& skip_w = "", int sk0 = -1, int sk1 = -1) {
     const int wi = m->conv_by_name.at(wname);
     const ConvW& w = m->convs[wi];
     const PT& a = T(in0);
@@ -306,6 +310,12 @@ struct Builder {
       l.out.stats = nullptr; l.out.slots = 0;
     }
     l.residual = residual >= 0 ? T(residual).ptr : nullptr;
+    if (!skip_w.empty()) {   // folded skip projection: extra K stages over the raw block input
+      op.skip_w = m->conv_by_name.at(skip_w);
+      l.sk0 = T(sk0);
+      if (sk1 >= 0) l.sk1 = T(sk1);
+      l.cin2_pad = m->convs[op.skip_w].cin_pad;
+    }
     if (xf != 0) {
       l.xf.enabled = 1;
       l.xf.silu = xf != 3;
@@ -389,11 +399,17 @@ struct Builder {
         // GroupNorm+SiLU and AdaGN+SiLU run inside the consumer convolutions (operand transform)
         const int h1 = conv(p + ".conv1", x0, x1, -1, 1.f, true, false, 1, m->raw_by_name.at(p + ".norm1.weight"));
         int res = x0, sk = -1;
+        std::string fold;
         if (m->conv_by_name.count(p + ".skip")) {
-          sk = conv(p + ".skip", x0, x1, -1, 1.f, false);
-          res = sk;
+          if (m->convs[m->conv_by_name.at(p + ".skip")].sk_planes > 0) {
+            fold = p + ".skip";      // runs inside conv2 (no launch, no skip tensor, no residual read)
+            res = -1;
+          } else {
+            sk = conv(p + ".skip", x0, x1, -1, 1.f, false);
+            res = sk;
+          }
         }
-        const int o = conv(p + ".conv2", h1, -1, res, rs, true, false, 2, -1, p + ".norm2.proj.1");
+        const int o = conv(p + ".conv2", h1, -1, res, rs, true, false, 2, -1, p + ".norm2.proj.1", fold, x0, x1);
         pl.release(h1);
         if (sk >= 0) pl.release(sk);
         pl.release(x0);
@@ -543,7 +559,7 @@ int r2dm_load_tensor(r2dm_handle h, const char* name_c, const float* src, const 
       if (n != static_cast<size_t>(c.cout) * c.cin * c.taps)
         return fail(-3, "%s: expected %d x %d x %d elements, got %zu", name_c, c.cout, c.cin, c.taps, n);
       CUDA_TRY(pack_conv_weight(h->dtype, c.taps, c.nt, src, c.cout, c.cin, c.cin_pad, c.cout_pad,
-                                h->arena + c.w_off, s));
+                                h->arena + c.w_off, s, c.sk_planes));
       c.w_ok = true;
     } else {
       if (n != static_cast<size_t>(c.cout)) return fail(-3, "%s: expected %d elements, got %zu", name_c, c.cout, n);
@@ -632,6 +648,11 @@ int r2dm_bind_workspace(r2dm_handle h, void* workspace, size_t bytes, int batch,
       const ConvW& w = h->convs[op.conv_w];
       op.conv.wpacked = h->arena + w.w_off;
       op.conv.bias = reinterpret_cast<const float*>(h->arena + w.b_off);
+      if (op.skip_w >= 0) {
+        const ConvW& sw = h->convs[op.skip_w];
+        op.conv.w2packed = h->arena + sw.w_off;
+        op.conv.bias2 = reinterpret_cast<const float*>(h->arena + sw.b_off);
+      }
       int rc = conv_make_tmaps(op.conv);
       if (rc) return fail(-4, "cuTensorMapEncodeTiled failed for %s (%d)", w.name.c_str(), rc);
       if (op.conv.xf.enabled && op.gn_gamma >= 0) {
@@ -780,6 +801,7 @@ int r2dm_profile_forward(r2dm_handle h, const float* x, const float* film, float
         const PT& o = op.conv.out;
         k = w.taps == 9 ? 1 : 2;
         fl = 2.0 * o.B * o.H * o.W * w.cin * w.cout * w.taps;
+        if (op.skip_w >= 0) fl += 2.0 * o.B * o.H * o.W * h->convs[op.skip_w].cin * w.cout;   // folded 1x1 skip
         by = static_cast<double>(o.B) * o.H * o.W * (w.cin * es + w.cout * (op.is_output ? 4.0 : es)) +
              static_cast<double>(w.cin) * w.cout * w.taps * es + (op.conv.residual ? static_cast<double>(o.B) * o.H * o.W * w.cout * es : 0.0);
         break;
