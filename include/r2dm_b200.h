@@ -11,6 +11,12 @@
  * (a cudaStream_t passed as void*) and never synchronises; every function returns 0 on success or
  * a negative code, with a message available from r2dm_last_error().  No function allocates device
  * memory: weights live in a caller-provided arena, activations in a caller-provided workspace.
+ *
+ * Devices and threads: a handle, its arena / workspace and every tensor passed with it belong to ONE CUDA
+ * device, which must be current in the calling thread.  One process may use several devices (per-device
+ * kernel attributes and SM counts are tracked inside the library); the intended deployment is one
+ * process per GPU (r2dm_b200/parallel.py).  r2dm_last_error() is thread-local; r2dm_set_option() and the
+ * r2dm_debug_* hooks are process-wide and not synchronised.
  */
 #ifndef R2DM_B200_H
 #define R2DM_B200_H
