@@ -162,6 +162,11 @@ int r2dm_op_conv(int dtype, int taps, const float* x, const float* w, const floa
 int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, const float* beta,
                     const float* film, float eps, int silu, const float* w, const float* bias, float* y,
                     int B, int Cin, int Cout, int H, int W, void* scratch, size_t scratch_bytes, void* stream);
+/* ResidualBlock tail with the skip projection folded into conv2 (efficient_unet.py:99-110 for blocks with a skip):
+ * y = (conv3x3(silu(adagn(h, film))) + bias + conv1x1(xs, w2) + bias2) * scale; h [B][C][H][W], xs [B][Cs][H][W] */
+int r2dm_op_gn_conv_skip(int dtype, const float* h, const float* film, float eps, const float* w, const float* bias,
+                         const float* xs, const float* w2, const float* bias2, float scale, float* y, int B, int C,
+                         int Cs, int H, int W, void* scratch, size_t scratch_bytes, void* stream);
 /* GroupNorm(8 groups) [+ FiLM: y = gn(x)*(1+fs)+fb when film_scale != NULL, per sample [B][C]] [+ SiLU] */
 int r2dm_op_groupnorm(int dtype, const float* x, const float* gamma, const float* beta,
                       const float* film_scale_shift, float eps, int silu, float* y, int B, int C, int H,

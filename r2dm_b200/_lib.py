@@ -86,6 +86,8 @@ _SIGS = {
                                C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "r2dm_op_gn_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, _P, _P, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "r2dm_op_gn_conv_skip": (C.c_int, [C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "r2dm_op_groupnorm": (C.c_int, [C.c_int, _P, _P, _P, _P, C.c_float, C.c_int, _P, C.c_int,
                                     C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "r2dm_op_resample": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P,

@@ -1028,6 +1028,55 @@ int r2dm_op_gn_conv(int dtype, int taps, const float* x, const float* gamma, con
   return 0;
 }
 
+// ResidualBlock tail with the folded skip projection, as the up-path blocks run it:
+//   y = (conv3x3(silu(adagn(h, film))) + bias + conv1x1(xs, w2) + bias2) * scale
+// h: [B][C][H][W] (C = Cout), xs: [B][Cs][H][W] raw block input, film: [B][2C], w: [C][C][3][3], w2: [C][Cs][1][1].
+int r2dm_op_gn_conv_skip(int dtype, const float* hsrc, const float* film, float eps, const float* w, const float* bias,
+                         const float* xs, const float* w2, const float* bias2, float scale, float* y, int B, int C,
+                         int Cs, int H, int W, void* scratch, size_t scratch_bytes, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (W % 128) return fail(-1, "W must be a multiple of 128");
+  if (C % (kNU * dtype_cw(dtype))) return fail(-1, "C must be a multiple of %d", kNU * dtype_cw(dtype));
+  Scratch sc{static_cast<uint8_t*>(scratch), scratch_bytes};
+  ConvLaunch l;
+  memset(&l, 0, sizeof(l));
+  l.dtype = dtype; l.taps = 9;
+  l.nt = pick_nt(C);
+  l.cin_pad = round_up(C, conv_stage_channels(dtype, 9));
+  if (l.cin_pad != C) return fail(-1, "C must be a multiple of the stage K");
+  l.cout = C; l.cout_pad = round_up(C, l.nt);
+  l.ht = (l.nt == 128) ? (H >= 2 ? 2 : 1) : (H % 4 == 0 ? 4 : (H >= 2 ? 2 : 1));
+  const int skp = conv_skip_planes(l.nt) * dtype_cw(dtype);
+  l.cin2_pad = round_up(Cs, skp);
+  if (l.cin2_pad != Cs) return fail(-1, "Cs must be a multiple of the skip stage K (%d)", skp);
+  PT probe; probe.B = B; probe.C = C; probe.H = H; probe.W = W;
+  l.in0 = make_pt(sc, dtype, B, C, H, W, tensor_stats_slots(dtype, probe));
+  l.sk0 = make_pt(sc, dtype, B, Cs, H, W, 0);
+  l.out = make_pt(sc, dtype, B, l.cout_pad, H, W, 0);
+  void* wp = sc.take(conv_packed_weight_bytes(dtype, 9, l.nt, l.cin_pad, l.cout_pad));
+  void* w2p = sc.take(conv_packed_weight_bytes(dtype, 1, l.nt, l.cin2_pad, l.cout_pad));
+  float* bp = static_cast<float*>(sc.take(static_cast<size_t>(l.cout_pad) * 4));
+  float* b2p = static_cast<float*>(sc.take(static_cast<size_t>(l.cout_pad) * 4));
+  if (!l.in0.ptr || !l.in0.stats || !l.sk0.ptr || !l.out.ptr || !wp || !w2p || !bp || !b2p) return fail(-1, "scratch too small");
+  CUDA_TRY(pack_nchw(dtype, hsrc, B, C, H, W, l.in0, 0, s));
+  CUDA_TRY(tensor_stats_launch(dtype, l.in0, s));
+  CUDA_TRY(pack_nchw(dtype, xs, B, Cs, H, W, l.sk0, 0, s));
+  CUDA_TRY(pack_conv_weight(dtype, 9, l.nt, w, C, C, l.cin_pad, l.cout_pad, wp, s));
+  CUDA_TRY(pack_conv_weight(dtype, 1, l.nt, w2, C, Cs, l.cin2_pad, l.cout_pad, w2p, s, conv_skip_planes(l.nt)));
+  CUDA_TRY(cudaMemsetAsync(bp, 0, static_cast<size_t>(l.cout_pad) * 4, s));
+  CUDA_TRY(cudaMemsetAsync(b2p, 0, static_cast<size_t>(l.cout_pad) * 4, s));
+  if (bias) CUDA_TRY(cudaMemcpyAsync(bp, bias, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, s));
+  if (bias2) CUDA_TRY(cudaMemcpyAsync(b2p, bias2, static_cast<size_t>(C) * 4, cudaMemcpyDeviceToDevice, s));
+  l.wpacked = wp; l.bias = bp; l.w2packed = w2p; l.bias2 = b2p; l.scale = scale;
+  l.xf.enabled = 1; l.xf.silu = 1; l.xf.groups = kNU; l.xf.eps = eps;
+  l.xf.film = film; l.xf.film_stride = 2 * C; l.xf.film_off = 0; l.xf.row_batch_stride = 1;
+  int rc = conv_make_tmaps(l);
+  if (rc) return fail(-4, "tensor map encode failed (%d)", rc);
+  CUDA_TRY(conv_launch(l, s));
+  CUDA_TRY(unpack_nchw(dtype, l.out, y, 0, C, s));
+  return 0;
+}
+
 int r2dm_op_groupnorm(int dtype, const float* x, const float* gamma, const float* beta, const float* film,
                       float eps, int silu, float* y, int B, int C, int H, int W, void* scratch,
                       size_t scratch_bytes, void* stream) {

@@ -60,6 +60,26 @@ def gn_conv2d(x, weight, bias=None, gamma=None, beta=None, film=None, eps=1e-6, 
     return y
 
 
+def gn_conv2d_skip(h, film, weight, bias, xs, skip_weight, skip_bias, scale, eps=1e-6, dtype="bf16"):
+    """ResidualBlock tail with the skip projection folded into conv2 (efficient_unet.py:99-110 on blocks with a
+    skip): (conv3x3(silu(adagn(h, film))) + bias + conv1x1(xs, skip_weight) + skip_bias) * scale."""
+    h, xs = L.f32c(h), L.f32c(xs)
+    w, w2 = L.f32c(weight), L.f32c(skip_weight)
+    B, Cc, H, W = h.shape
+    Cs = xs.shape[1]
+    assert w.shape == (Cc, Cc, 3, 3) and w2.shape[:2] == (Cc, Cs)
+    b = L.f32c(bias) if bias is not None else None
+    b2 = L.f32c(skip_bias) if skip_bias is not None else None
+    f = L.f32c(film)
+    y = torch.empty(B, Cc, H, W, device=h.device, dtype=torch.float32)
+    n = 2 * L.lib().r2dm_op_scratch_bytes(B, max(Cc, Cs), H, W)
+    sc = torch.empty(n, dtype=torch.uint8, device=h.device)
+    L.check(L.lib().r2dm_op_gn_conv_skip(_dt(dtype), L.ptr(h), L.ptr(f), float(eps), L.ptr(w), L.ptr(b), L.ptr(xs),
+                                         L.ptr(w2), L.ptr(b2), float(scale), L.ptr(y), B, Cc, Cs, H, W, L.ptr(sc), n,
+                                         L.stream_ptr()), "r2dm_op_gn_conv_skip")
+    return y
+
+
 def group_norm(x, gamma=None, beta=None, film=None, eps=1e-6, silu=False, dtype="bf16"):
     """nn.GroupNorm(8, C, eps) (+SiLU); with `film` [B, 2C] = [scale || shift]: AdaGN (ops.py:196-199)."""
     x = L.f32c(x)

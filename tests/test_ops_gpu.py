@@ -48,6 +48,11 @@ CONV_CASES = [
     (1, 256, 256, 2, 128, 1, True),
     (2, 128, 256, 4, 256, 3, True),
     (1, 64, 512, 2, 128, 3, False),
+    # full-resolution shapes of config H (four-row tiles across the whole 64 x 1024 image, 7 tiles per CTA;
+    # two-row 128-channel tiles at 32 x 512; single-row tiles at the 8 x 128 bottleneck)
+    (2, 64, 64, 64, 1024, 3, True),
+    (2, 128, 128, 32, 512, 3, True),
+    (4, 512, 512, 8, 128, 3, False),
 ]
 
 
@@ -155,3 +160,39 @@ def test_fused_groupnorm_conv(case, dtype):
     e = rel_l2(y, ref)
     tol = 6e-3 if dtype == "bf16" else 1e-3
     assert e <= tol, f"fused gn+conv {case}[{dtype}]: l2-rel {e:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 1024, 3, True), (2, 128, 128, 32, 512, 3, False)])
+def test_fused_groupnorm_conv_full_resolution(case, dtype):
+    """The fused form at config H's real tile counts (several tiles per CTA, image changes inside a CTA's
+    range, statistics folded from 128 slots)."""
+    test_fused_groupnorm_conv(case, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
+@pytest.mark.parametrize("case", [
+    # B, C, Cs, H, W  (the four up-path skip shapes of config H, at reduced and at full size)
+    (2, 64, 128, 8, 256), (1, 64, 256, 4, 128), (2, 128, 512, 4, 256), (1, 256, 512, 2, 128), (3, 256, 512, 8, 128),
+    (2, 64, 128, 64, 1024), (2, 128, 512, 16, 256),
+])
+def test_folded_skip_projection(case, dtype):
+    """ResidualBlock tail of the up-path blocks (efficient_unet.py:99-110): the 1x1 skip projection runs as extra
+    K stages of conv2 - (conv3x3(silu(adagn(h))) + b + conv1x1(x) + b_skip) / sqrt 2 - against the oracle ops."""
+    from r2dm_b200 import ops
+    B, Cc, Cs, H, W = case
+    g = torch.Generator().manual_seed(17)
+    h = _round_to(torch.randn(B, Cc, H, W, generator=g) * 1.3 + 0.2, dtype)
+    xs = _round_to(torch.randn(B, Cs, H, W, generator=g), dtype)
+    w = _round_to(torch.randn(Cc, Cc, 3, 3, generator=g) / math.sqrt(Cc * 9), dtype)
+    w2 = _round_to(torch.randn(Cc, Cs, 1, 1, generator=g) / math.sqrt(Cs), dtype)
+    b, b2 = torch.randn(Cc, generator=g) * 0.1, torch.randn(Cc, generator=g) * 0.1
+    ss = torch.randn(B, 2 * Cc, generator=g) * 0.3
+    scale = 1 / math.sqrt(2)
+    hn = O.group_norm(h, 8, 1e-6, None, None) * (1 + ss[:, :Cc, None, None]) + ss[:, Cc:, None, None]
+    ref = (O.ring_conv3x3(torch.nn.functional.silu(hn), w, b) + O.conv1x1(xs, w2, b2)) * scale
+    y = ops.gn_conv2d_skip(h.cuda(), ss.cuda(), w.cuda(), b.cuda(), xs.cuda(), w2.cuda(), b2.cuda(), scale, dtype=dtype)
+    torch.cuda.synchronize()
+    e = rel_l2(y, ref)
+    tol = 6e-3 if dtype == "bf16" else 1e-3
+    assert e <= tol, f"folded skip {case}[{dtype}]: l2-rel {e:.3e} > {tol}"

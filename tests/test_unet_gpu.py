@@ -72,6 +72,25 @@ def test_batch_composition_invariance():
     assert torch.equal(y3[1:2], y1), "batch split changed a sample's result"
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_batch_composition_invariance_config_h_b8(precision):
+    """The benchmarked shape: config H, batch 8.  Every sample of the batch-8 forward equals its own batch-1
+    forward bit for bit (tile shapes and summation orders never depend on the batch), so the B=1 golden
+    parity of config H carries over to B=8."""
+    from tests.helpers import H_CFG
+    sd = O.random_state_dict(H_CFG, 1234)
+    ddpm = make_ddpm(H_CFG, sd, precision=precision)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(8, 2, *H_CFG.resolution, generator=g).cuda()
+    cond = torch.linspace(-12.0, 12.0, 8).cuda()
+    y8 = ddpm.model(x, cond).clone()
+    for i in (0, 3, 7):
+        y1 = ddpm.model(x[i:i + 1].contiguous(), cond[i:i + 1])
+        assert torch.equal(y8[i:i + 1], y1), f"sample {i} differs between B=8 and B=1"
+    ref = O.unet_forward(sd, H_CFG, x[5:6].cpu(), cond[5:6].cpu())
+    assert rel_l2(y8[5:6], ref) <= TOL[precision]
+
+
 def test_scalar_timestep_broadcast_and_autocast():
     cfg = SMALL_CFG
     sd = O.random_state_dict(cfg, 3)
