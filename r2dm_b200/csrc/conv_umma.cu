@@ -496,7 +496,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     const int m = q * 32 + lane;
     const int Wp = p.W + 2;
     const int planes_out = p.cout_pad / CW;
-    const size_t plane_stride = static_cast<size_t>(p.H) * Wp;   // 16-byte units between channel planes
+    // 16-byte units between channel planes; unit indices fit in 32 bits (a tensor of 2^32 units would be 64 GB)
+    const uint32_t plane_stride = static_cast<uint32_t>(p.H) * static_cast<uint32_t>(Wp);
     constexpr int CB = NT >= 32 ? 32 : 16;              // columns per chunk
     constexpr int CCOLS = HT > 1 ? NT : NT / 2;         // columns visited by this warp
     constexpr int NCHUNK = CCOLS / CB;
@@ -550,7 +551,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int r = r_begin; r < HT; r += RSTEP) {
           const int y = y0 + r;
           if (y < p.H) {
-            const size_t idx0 = pt_index(b, planes_out, (n0 + c0) / CW, p.H, Wp, y, x + 1);
+            const uint32_t idx0 = static_cast<uint32_t>(pt_index(b, planes_out, (n0 + c0) / CW, p.H, Wp, y, x + 1));
             // residual prefetch (independent loads in flight while TMEM is read)
             uint4 rr[CB / CW];
             if (!NCHW && res != nullptr) {
@@ -583,8 +584,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               constexpr int PPU = CW / 2;                   // pairs per 16-byte unit
 #pragma unroll
               for (int u = 0; u < CB / CW; ++u) {
-                const size_t idx = idx0 + u * plane_stride;
-                f32x2* o2 = v2 + u * PPU;
+                const uint32_t idx = idx0 + u * plane_stride;
+                f32x2 o2[PPU];
+#pragma unroll
+                for (int i = 0; i < PPU; ++i) o2[i] = v2[u * PPU + i];
                 if (res != nullptr) {
                   f32x2 r2[PPU];
                   Elem<T>::unpack2x(rr[u], r2);
