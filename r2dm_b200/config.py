@@ -15,6 +15,8 @@ def _coerce(cls, value):
     if value is None:
         return cls()
     if isinstance(value, dict):
+        if cls is TrainingConfig:
+            return cls(**value)
         known = {f.name for f in fields(cls)}
         return cls(**{k: v for k, v in value.items() if k in known})
     raise TypeError(f"cannot build {cls.__name__} from {type(value).__name__}")
@@ -48,27 +50,28 @@ class DiffusionConfig:
     timestep_type: str = "continuous"
 
 
-@dataclass
 class TrainingConfig:
-    batch_size_train: int = 8
-    batch_size_eval: int = 8
-    num_workers: int = 4
-    num_steps: int = 300_000
-    steps_save_image: int = 5_000
-    steps_save_model: int = 10_000
-    gradient_accumulation_steps: int = 1
-    lr: float = 1e-4
-    lr_warmup_steps: int = 10_000
-    adam_beta1: float = 0.9
-    adam_beta2: float = 0.99
-    adam_weight_decay: float = 0.0
-    adam_epsilon: float = 1e-8
-    ema_decay: float = 0.995
-    ema_update_every: int = 10
-    mixed_precision: Optional[str] = "fp16"
-    dynamo_backend: Optional[str] = "inductor"
-    output_dir: str = "logs/diffusion"
-    seed: int = 0
+    """Training settings of a checkpoint (optimizer, EMA, mixed precision, ...; utils/option.py:31-50).
+    Training is outside the scope of this package, so the section is carried through opaquely: whatever keys
+    the checkpoint holds are kept, readable as attributes, and written back unchanged by `Config.to_dict()`."""
+
+    # the two settings the sampling scripts look at (sample_and_save.py:25-27), with the reference's defaults
+    _DEFAULTS = {"mixed_precision": "fp16", "dynamo_backend": "inductor"}
+
+    def __init__(self, **settings):
+        self.settings = {**self._DEFAULTS, **settings}
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["settings"][name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __eq__(self, other):
+        return isinstance(other, TrainingConfig) and self.settings == other.settings
+
+    def __repr__(self):
+        return f"TrainingConfig({self.settings})"
 
 
 @dataclass
@@ -101,4 +104,5 @@ class Config:
         self.training = _coerce(TrainingConfig, self.training)
 
     def to_dict(self) -> dict:
-        return asdict(self)
+        return {"data": asdict(self.data), "model": asdict(self.model), "diffusion": asdict(self.diffusion),
+                "training": dict(self.training.settings)}
