@@ -76,11 +76,23 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// Developer instrumentation (role timelines, ablation knobs) is compiled in only with -DR2DM_DEV=1
+// (tools/trace_conv.py, tools/trace_forward.py need such a build): in the product build the checks would cost a
+// few instructions per pipeline stage in every role.
+#ifndef R2DM_DEV
+#define R2DM_DEV 0
+#endif
+#if R2DM_DEV
 #define R2DM_TRACE(role, idx)                                                          \
   do {                                                                                 \
     if (p.trace != nullptr && blockIdx.x == p.trace_block && (idx) < p.trace_cap)      \
       p.trace[(role) * p.trace_cap + (idx)] = static_cast<unsigned long long>(clock64()); \
   } while (0)
+#define R2DM_DBG(expr) (expr)
+#else
+#define R2DM_TRACE(role, idx) do { } while (0)
+#define R2DM_DBG(expr) 0
+#endif
 
 __device__ __forceinline__ float silu_from_half(float h) {
   float th;

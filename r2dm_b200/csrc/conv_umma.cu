@@ -110,7 +110,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  if (p.trace != nullptr && blockIdx.x == p.trace_block && threadIdx.x == 0 && p.trace_cap >= 8) {
+  if (R2DM_DBG(p.trace != nullptr && blockIdx.x == p.trace_block && threadIdx.x == 0 && p.trace_cap >= 8)) {
     p.trace[p.trace_cap - 4] = static_cast<unsigned long long>(clock64());   // (clock, globaltimer) at start
     p.trace[p.trace_cap - 3] = gtime();
   }
@@ -150,7 +150,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int ks = 0; ks < p.nk; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
           mbar_wait_relaxed(&empty_bar[st], ph ^ 1, 2000);
           uint8_t* sa = smem_ring + static_cast<size_t>(st) * p.stage_bytes;
-          if (p.debug & 4) { mbar_arrive(&full_bar[st]); continue; }
+          if (R2DM_DBG(p.debug & 4)) { mbar_arrive(&full_bar[st]); continue; }
           mbar_expect_tx(&full_bar[st], Tr::A_BYTES + (p.wres ? 0 : Tr::B_BYTES));
           const bool second = ks >= p.ksplit;
           const int plane0 = (second ? ks - p.ksplit : ks) * Tr::PLANES;
@@ -208,7 +208,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           const uint32_t a_lo0 = a_lo_const | ((sa >> 4) & 0x3FFFu);
           const uint32_t b_lo0 = b_lo_const | ((sb >> 4) & 0x3FFFu);
           constexpr uint32_t kHi = (128u >> 4) | (1u << 14);
-          if (p.debug & 2) {
+          if (R2DM_DBG(p.debug & 2)) {
             // developer ablation: no MMAs issued
           } else if constexpr (Tr::FUSE) {
 #pragma unroll
@@ -324,7 +324,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       for (int t = t_begin; t < t_end; ++t) {
         int b, yt, xt, nt;
         decode(t, b, yt, xt, nt);
-        if (b != cur_b && !(p.xf.debug & 4)) {   // (debug 4: developer ablation, no statistics fold)
+        if (b != cur_b && !R2DM_DBG(p.xf.debug & 4)) {   // (debug 4: developer ablation, no statistics fold)
           // ---- fold statistics + affine/FiLM into per-channel (a, d) for image b (all 8 warps; the
           // first barrier also guarantees that nobody still reads the previous image's table)
           cur_b = b;
@@ -453,7 +453,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             for (int k = 0; k < CW / 2; ++k) unpack2(v2[k], v[2 * k], v[2 * k + 1]);
             return Elem<T>::pack_mma(v);
           };
-          if (c0 < Ctot && p.xf.debug == 0) {
+          if (c0 < Ctot && !R2DM_DBG(p.xf.debug != 0)) {
             // full batches of XB units per thread: all loads first, then the math, then the stores;
             // the remainder (n_units is not a multiple of XB * TPP) goes one unit at a time so that no
             // XU-pipe slots are spent on padding
@@ -539,7 +539,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       if (ethread == 0) R2DM_TRACE(3, 3 * j);
       const uint32_t tbase = tmem + buf * Tr::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int ch = 0; ch < ((p.debug & 1) ? 0 : NCHUNK); ++ch) {
+      for (int ch = 0; ch < (R2DM_DBG(p.debug & 1) ? 0 : NCHUNK); ++ch) {
         const int c0 = c_begin + ch * CB;
         // partial (sum, sum of squares) of this warp's pixels per 8-channel sub-chunk, as fp32 pairs over
         // (even, odd) channels: packed FADD2 / FFMA2, one issue slot per two values
@@ -556,7 +556,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             uint4 rr[CB / CW];
             if (!NCHW && res != nullptr) {
 #pragma unroll
-              for (int u = 0; u < CB / CW; ++u) rr[u] = (p.debug & 8) ? make_uint4(0u, 0u, 0u, 0u) : res[idx0 + u * plane_stride];
+              for (int u = 0; u < CB / CW; ++u) rr[u] = R2DM_DBG(p.debug & 8) ? make_uint4(0u, 0u, 0u, 0u) : res[idx0 + u * plane_stride];
             }
             float v[CB];
 #pragma unroll
@@ -675,7 +675,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (p.trace != nullptr && blockIdx.x == p.trace_block && threadIdx.x == 0 && p.trace_cap >= 8) {
+  if (R2DM_DBG(p.trace != nullptr && blockIdx.x == p.trace_block && threadIdx.x == 0 && p.trace_cap >= 8)) {
     p.trace[p.trace_cap - 2] = static_cast<unsigned long long>(clock64());   // ... and at the end: SM clock rate
     p.trace[p.trace_cap - 1] = gtime();
   }

@@ -1,4 +1,6 @@
-"""Developer tool: per-role timeline of CTA 0 of one fused conv launch (config-H shapes).
+"""[needs a library built with EXTRA_FLAGS="-DR2DM_DEV=1" ./build.sh - the role traces and the
+R2DM_CONV_DEBUG / R2DM_XF_DEBUG ablation knobs are compiled out of the product build]
+Developer tool: per-role timeline of CTA 0 of one fused conv launch (config-H shapes).
 Usage: python tools/trace_conv.py [Cin Cout H W [gn]]   (gn=0: no fused GroupNorm transform)"""
 import os, sys
 import torch

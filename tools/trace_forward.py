@@ -1,4 +1,6 @@
-"""Developer tool: role timeline of ONE conv launch inside steady-state forwards (warm clocks, real
+"""[needs a library built with EXTRA_FLAGS="-DR2DM_DEV=1" ./build.sh - the role traces and the
+R2DM_CONV_DEBUG / R2DM_XF_DEBUG ablation knobs are compiled out of the product build]
+Developer tool: role timeline of ONE conv launch inside steady-state forwards (warm clocks, real
 predecessors).  Usage: R2DM_TRACE_SKIP=<k> python tools/trace_forward.py   traces the (k+1)-th conv_umma launch
 after 5 warm-up forwards (conv launch order within a forward: see profiles/r01_conv_dram_v4.txt; 64 per forward)."""
 import os, sys
