@@ -515,7 +515,10 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
       decode(t, b, yt, xt, nt);
       const int n0 = nt * NT, x = xt * 128 + m, y0 = yt * HT;
       const int buf = j & 1, par = j & 1;
-      const bool edge_warp = (xt == 0 && q == 0) || (xt == p.xtiles - 1 && q == 3);   // holds pixel 0 or W-1
+      // the thread that holds pixel 0 (W-1) also writes the wrap halo column xp = W+1 (xp = 0): one predicated
+      // store at a signed offset, no divergent block inside the unit loop
+      const bool seam = (x == 0) || (x == p.W - 1);
+      const int seam_off = (x == 0) ? p.W : -p.W;
       if (nt != cur_nt) {   // bias of this N tile -> shared memory (once per CTA when ntiles == 1)
         cur_nt = nt;
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -602,10 +605,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 }
                 const uint4 pk = Elem<T>::pack2x(o2);
                 out[idx] = pk;
-                if (edge_warp) {                              // warp-uniform: only the two warps at the seam
-                  if (x == 0) out[idx + p.W] = pk;            // xp = W+1 mirrors pixel 0
-                  if (x == p.W - 1) out[idx - p.W] = pk;      // xp = 0 mirrors pixel W-1
-                }
+                if (seam) out[static_cast<int>(idx) + seam_off] = pk;
               }
             }
           }
