@@ -410,16 +410,16 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         const int n_units = (row_hi - row_lo) * Tr::APITCH;
         for (int ks = 0; ks < p.nk; ++ks, ++it, st = (st + 1 == p.stages ? 0 : st + 1), ph ^= (st == 0 ? 1u : 0u)) {
           if ((it & 1u) != static_cast<uint32_t>(grp)) continue;
-          // per-channel coefficients of this thread's plane as fp32 pairs (channels 2i, 2i+1)
+          // per-channel coefficients of this thread's plane as fp32 pairs (channels 2i, 2i+1); every plane of a
+          // transformed layer is real (the host rejects channel padding together with the transform)
           f32x2 ca2[CW / 2], cd2[CW / 2];
           const int c0 = (ks * Tr::PLANES + my_plane) * CW;
 #pragma unroll
-          for (int i = 0; i < CW / 2; ++i) {
-            const bool ok = c0 + 2 * i < Ctot;     // Ctot is a multiple of CW: a plane is all real or all padding
-            const float2 a = ok ? *reinterpret_cast<const float2*>(coef_a + c0 + 2 * i) : make_float2(0.f, 0.f);
-            const float2 d = ok ? *reinterpret_cast<const float2*>(coef_d + c0 + 2 * i) : make_float2(0.f, 0.f);
-            ca2[i] = pack2(a.x, a.y);
-            cd2[i] = pack2(d.x, d.y);
+          for (int i = 0; i < CW / 4; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(coef_a + c0 + 4 * i);
+            const float4 d = *reinterpret_cast<const float4*>(coef_d + c0 + 4 * i);
+            ca2[2 * i] = pack2(a.x, a.y); ca2[2 * i + 1] = pack2(a.z, a.w);
+            cd2[2 * i] = pack2(d.x, d.y); cd2[2 * i + 1] = pack2(d.z, d.w);
           }
           mbar_wait_relaxed(&full_bar[st], ph, 500);
           if (tt == 0) R2DM_TRACE(grp ? 4 : 2, 2 * it);
@@ -453,7 +453,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             for (int k = 0; k < CW / 2; ++k) unpack2(v2[k], v[2 * k], v[2 * k + 1]);
             return Elem<T>::pack_mma(v);
           };
-          if (c0 < Ctot && !R2DM_DBG(p.xf.debug != 0)) {
+          if (!R2DM_DBG(p.xf.debug != 0)) {
             // full batches of XB units per thread: all loads first, then the math, then the stores;
             // the remainder (n_units is not a multiple of XB * TPP) goes one unit at a time so that no
             // XU-pipe slots are spent on padding
@@ -537,6 +537,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           }
         }
       }
+      // unit index of (image b, plane of channel n0, row y0, this thread's pixel); rows and planes are offsets from it
+      const uint32_t tile_idx = static_cast<uint32_t>(pt_index(b, planes_out, n0 / CW, p.H, Wp, y0, x + 1));
       mbar_wait_relaxed(&acc_full[buf], (j >> 1) & 1, 1000);
       tc_fence_after();
       if (ethread == 0) R2DM_TRACE(3, 3 * j);
@@ -554,7 +556,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int r = r_begin; r < HT; r += RSTEP) {
           const int y = y0 + r;
           if (y < p.H) {
-            const uint32_t idx0 = static_cast<uint32_t>(pt_index(b, planes_out, (n0 + c0) / CW, p.H, Wp, y, x + 1));
+            const uint32_t idx0 = tile_idx + static_cast<uint32_t>(r) * static_cast<uint32_t>(Wp) +
+                                  static_cast<uint32_t>(c0 / CW) * plane_stride;
             // residual prefetch (independent loads in flight while TMEM is read)
             uint4 rr[CB / CW];
             if (!NCHW && res != nullptr) {
@@ -839,6 +842,7 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
     if (dbg < 0) { const char* e = getenv("R2DM_XF_DEBUG"); dbg = e ? atoi(e) : 0; }
     x.debug = dbg;
     if (x.C0 + x.C1 > kMaxCin || x.stats0 == nullptr) return cudaErrorInvalidValue;
+    if (x.C0 + x.C1 != l.cin_pad) return cudaErrorInvalidValue;   // no channel padding under the transform
   }
   // shared-memory plan: resident weights when the whole bank of this N tile fits, then as many
   // ring stages as the budget allows
