@@ -150,6 +150,25 @@ int r2dm_philox_normal(float* out, const r2dm_philox* philox, int draw, int batc
 int r2dm_lidar_postprocess(const float* sample, const float* angles, float* out, int batch, int H,
                            int W, int depth_format, float min_depth, float max_depth, void* stream);
 
+/* --- caller-side consumers of the generated point clouds -------------------
+ * utils/render.py:32-80 render_point_clouds: points [B][N][3] (already divided by max_depth by the caller),
+ * colors [B][N][3] or NULL (= white), R [3][3] row-major applied as p @ R or NULL, t [3] or NULL ->
+ * out [B][3][size][size].  acc: scratch of B*size*size*16 bytes (weighted colour / weight sums). */
+int r2dm_render_point_clouds(const float* points, const float* colors, const float* R, const float* t, float* acc,
+                             float* out, int batch, int num_points, int size, float focal_length, void* stream);
+/* utils/render.py:83-142 bilinear_rasterizer: coords [B][N][2] = (row, column), values [B][N][C] ->
+ * out [B][C][H][W] (four-neighbour scatter-add, weights below 1e-3 and neighbours outside dropped). */
+int r2dm_bilinear_rasterize(const float* coords, const float* values, float* out, int batch, int num_points,
+                            int channels, int H, int W, void* stream);
+/* utils/render.py:145-234 estimate_surface_normal: points [B][3][H][W] -> unit normals [B][3][H][W];
+ * d = neighbour distance, mode 0 "closest", 1 "mean". */
+int r2dm_surface_normal(const float* points, float* out, int batch, int H, int W, int d, int mode, void* stream);
+/* metrics/bev.py:5-24 point_cloud_to_histogram, batched: points [B][N][3], edges [bins+1] (bin edges of both
+ * axes, as torch.histogramdd builds them) -> hist [B][bins][bins] (fp32 counts of x-bin, y-bin);
+ * counts: scratch of B*bins*bins uint32. */
+int r2dm_bev_histogram(const float* points, const float* edges, unsigned int* counts, float* hist, int batch,
+                       int num_points, int bins, float min_depth, float max_depth, void* stream);
+
 /* --- single-operator entry points (used by the parity tests; same kernels as the network) ----------
  * All take fp32 NCHW tensors and a scratch buffer for the packed intermediates. */
 size_t r2dm_op_scratch_bytes(int batch, int max_channels, int H, int W);

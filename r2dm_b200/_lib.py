@@ -81,6 +81,10 @@ _SIGS = {
     "r2dm_philox_normal": (C.c_int, [_P, C.POINTER(R2dmPhilox), C.c_int, C.c_int, C.c_size_t, _P]),
     "r2dm_lidar_postprocess": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_float, _P]),
+    "r2dm_render_point_clouds": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "r2dm_bilinear_rasterize": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "r2dm_surface_normal": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "r2dm_bev_histogram": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
     "r2dm_op_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "r2dm_op_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),

@@ -201,4 +201,14 @@ cudaError_t lidar_postprocess_launch(const float* sample, const float* angles, f
                                      int H, int W, int depth_format, float min_depth,
                                      float max_depth, cudaStream_t s);
 
+// caller-side consumers of the generated point clouds (render.cu; utils/render.py, metrics/bev.py)
+cudaError_t render_splat_launch(const float* points, const float* colors, const float* R, const float* t,
+                                float* acc, float* out, int B, int N, int size, float focal, cudaStream_t s);
+cudaError_t rasterize_launch(const float* coords, const float* values, float* out, int B, int N, int C, int H, int W,
+                             cudaStream_t s);
+cudaError_t surface_normal_launch(const float* points, float* out, int B, int H, int W, int d, int mode,
+                                  cudaStream_t s);
+cudaError_t bev_histogram_launch(const float* points, const float* edges, unsigned int* counts, float* hist, int B,
+                                 int N, int bins, float min_depth, float max_depth, cudaStream_t s);
+
 }  // namespace r2dm

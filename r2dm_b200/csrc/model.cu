@@ -923,6 +923,42 @@ int r2dm_lidar_postprocess(const float* sample, const float* angles, float* out,
   return 0;
 }
 
+// ---------------------------------------------------------------------------------- caller-side consumers
+int r2dm_render_point_clouds(const float* points, const float* colors, const float* R, const float* t, float* acc,
+                             float* out, int batch, int num_points, int size, float focal_length, void* stream) {
+  if (!points || !acc || !out) return fail(-1, "null argument");
+  if (batch < 1 || num_points < 1 || size < 2 || size > 4096) return fail(-1, "bad batch / num_points / size");
+  CUDA_TRY(render_splat_launch(points, colors, R, t, acc, out, batch, num_points, size, focal_length,
+                               static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_bilinear_rasterize(const float* coords, const float* values, float* out, int batch, int num_points,
+                            int channels, int H, int W, void* stream) {
+  if (!coords || !values || !out) return fail(-1, "null argument");
+  if (batch < 1 || num_points < 1 || channels < 1 || H < 1 || W < 1 || static_cast<long long>(H) * W > (1 << 24))
+    return fail(-1, "bad shape (H * W must stay below 2^24: the reference computes pixel indices in fp32)");
+  CUDA_TRY(rasterize_launch(coords, values, out, batch, num_points, channels, H, W, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_surface_normal(const float* points, float* out, int batch, int H, int W, int d, int mode, void* stream) {
+  if (!points || !out) return fail(-1, "null argument");
+  if (batch < 1 || H < 1 || W < 1 || d < 1 || d > W) return fail(-1, "bad shape / neighbour distance");
+  if (mode != 0 && mode != 1) return fail(-1, "mode must be 0 (closest) or 1 (mean)");
+  CUDA_TRY(surface_normal_launch(points, out, batch, H, W, d, mode, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int r2dm_bev_histogram(const float* points, const float* edges, unsigned int* counts, float* hist, int batch,
+                       int num_points, int bins, float min_depth, float max_depth, void* stream) {
+  if (!points || !edges || !counts || !hist) return fail(-1, "null argument");
+  if (batch < 1 || num_points < 1 || bins < 1) return fail(-1, "bad shape");
+  CUDA_TRY(bev_histogram_launch(points, edges, counts, hist, batch, num_points, bins, min_depth, max_depth,
+                                static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------- op hooks
 namespace {
 struct Scratch {
