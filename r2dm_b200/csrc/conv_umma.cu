@@ -606,7 +606,13 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                   s1p[sub] = add2(s1p[sub], o2[i]);
                   s2p[sub] = fma2(o2[i], o2[i], s2p[sub]);
                 }
-                const uint4 pk = Elem<T>::pack2x(o2);
+                uint4 pk = Elem<T>::pack2x(o2);
+                if (sizeof(T) == 4 && p.round_out) {
+                  asm("cvt.rna.tf32.f32 %0, %0;" : "+r"(pk.x));
+                  asm("cvt.rna.tf32.f32 %0, %0;" : "+r"(pk.y));
+                  asm("cvt.rna.tf32.f32 %0, %0;" : "+r"(pk.z));
+                  asm("cvt.rna.tf32.f32 %0, %0;" : "+r"(pk.w));
+                }
                 out[idx] = pk;
                 if (seam) out[static_cast<int>(idx) + seam_off] = pk;
               }
@@ -735,10 +741,12 @@ static int make_one_tmap(CUtensorMap* tm, int dtype, const PT& t, int box_w, int
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
-// qkv tensor map for the attention kernel: box = 128 pixels of one row x (hd/8) planes
-int attention_make_tmap(CUtensorMap* tm, const PT& qkv, int heads) {
+// qkv tensor maps for the attention kernel: boxes of 128 (Q) / key-tile (K, V) pixels of one row x (hd/CW) planes
+int attention_make_tmaps(CUtensorMap* tm_q, CUtensorMap* tm_kv, int dtype, const PT& qkv, int heads) {
   const int hd = qkv.C / 3 / heads;
-  return make_one_tmap(tm, kBF16, qkv, 128, 1, hd / 8);
+  int rc = make_one_tmap(tm_q, dtype, qkv, 128, 1, hd / dtype_cw(dtype));
+  if (rc) return rc;
+  return make_one_tmap(tm_kv, dtype, qkv, attention_key_tile(dtype), 1, hd / dtype_cw(dtype));
 }
 
 int conv_make_tmaps(ConvLaunch& l) {
@@ -854,6 +862,7 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.coef_ch = l.xf.enabled ? (p.xf.C0 + p.xf.C1 + 31) / 32 * 32 : 0;
   p.coef_bytes = 2 * p.coef_ch * static_cast<int>(sizeof(float));
   p.reverse = l.reverse;
+  p.round_out = l.round_out;
   p.ktime = l.ktime;
   const int avail = kSmemBudget - 256 - p.coef_bytes - (p.wres ? static_cast<int>(wbytes) : 0);
   int stages = avail / p.stage_bytes;

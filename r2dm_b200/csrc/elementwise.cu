@@ -294,50 +294,121 @@ cudaError_t gn_apply_launch(const GnApply& g, cudaStream_t s) {
 }
 
 // =============================================================================== FIR resampling
+// Both resamplers are bound by load / store instruction issue, not by DRAM (ncu, round 1: 25-38 % of DRAM peak at
+// 60 % SM busy with one 16-byte access per tap), so the round-2 versions are organised around the fewest and
+// widest accesses: a thread owns a 32-byte-aligned PAIR of 16-byte units of the wider tensor (one 256-bit
+// LDG / STG, a warp touches 1 KB contiguous), gets its horizontal neighbour from the next lane with shuffles
+// (the last lane of a warp loads it), and walks several rows so that every input row is loaded once per block.
+// The arithmetic (order of the FMAs) is unchanged from round 1, so the results are bit-identical.
+struct U256 { uint4 a, b; };
+__device__ __forceinline__ U256 ldg256(const uint4* p) {   // p must be 32-byte aligned
+  U256 r;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(uint4* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 shfl_down1(const uint4& v) {
+  return make_uint4(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1),
+                    __shfl_down_sync(0xffffffffu, v.z, 1), __shfl_down_sync(0xffffffffu, v.w, 1));
+}
+
 // ops.Resample(down=2) (models/ops.py:52-146) in closed form:
 //   y[i,j] = sum_{a,b<4} w_a w_b x[2i-1+a, 2j-1+b],  w = [1,3,3,1]/8, W circular, H zero padded.
-// One block = one output row segment of 128 pixels of one plane; emits GroupNorm partials.
+// One block = R output rows x 128 output pixels of one plane: thread j owns the padded input pair (2j, 2j+1)
+// (taps b = 0, 1; taps 2, 3 are the next lane's pair), filters each of the 2R+2 input rows horizontally once and
+// feeds it to the two output rows it belongs to.  Emits GroupNorm partials (one slot per block).
 template <typename T>
 __global__ void __launch_bounds__(128) down2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int planes,
                                                     int Hi, int Wi, float* __restrict__ stats, int slots,
-                                                    int planes_per_unit) {
+                                                    int planes_per_unit, int R) {
   pdl_launch_dependents();   // PDL: let the next kernel become resident; wait for the previous one's results
   pdl_wait();
   constexpr int CW = Elem<T>::CW;
   const int Ho = Hi / 2, Wo = Wi / 2;
   const int xsegs = Wo / 128;
-  const int xo = (blockIdx.x % xsegs) * 128 + threadIdx.x, yo = blockIdx.x / xsegs;
+  const int xo = (blockIdx.x % xsegs) * 128 + threadIdx.x, yo0 = (blockIdx.x / xsegs) * R;
   const int pl = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31;
   const float w[4] = {0.125f, 0.375f, 0.375f, 0.125f};
-  float acc[CW];
+  const uint4* col = src + pt_index(b, planes, pl, Hi, Wi + 2, 0, 2 * xo);   // padded units 2xo, 2xo+1 of row 0
+  const size_t out0 = pt_index(b, planes, pl, Ho, Wo + 2, 0, xo + 1);
+  float cur[CW], prev[CW];
 #pragma unroll
-  for (int i = 0; i < CW; ++i) acc[i] = 0.f;
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int yi = 2 * yo - 1 + a;
-    if (yi < 0 || yi >= Hi) continue;
-    float row[CW];
+  for (int i = 0; i < CW; ++i) { cur[i] = 0.f; prev[i] = 0.f; }
+  float s1 = 0.f, s2 = 0.f;
+  // Input rows are visited in pairs (both loads of a pair are in flight together): pair m = image rows
+  // 2 (yo0 + m) - 1 and 2 (yo0 + m) carries taps 0, 1 of output yo0 + m (cur) and taps 2, 3 of output yo0 + m - 1
+  // (prev), which is complete afterwards.  Same FMA order as one tap at a time.
+  auto hfilter = [&](const U256& own, const U256& nb, float* row) {
+    float v[CW];
 #pragma unroll
     for (int i = 0; i < CW; ++i) row[i] = 0.f;
+    Elem<T>::unpack(own.a, v);
 #pragma unroll
-    for (int bb = 0; bb < 4; ++bb) {
-      float v[CW];
-      Elem<T>::unpack(src[pt_index(b, planes, pl, Hi, Wi + 2, yi, 2 * xo + bb)], v);  // xp = 2xo-1+bb+1
+    for (int i = 0; i < CW; ++i) row[i] = fmaf(w[0], v[i], row[i]);
+    Elem<T>::unpack(own.b, v);
 #pragma unroll
-      for (int i = 0; i < CW; ++i) row[i] = fmaf(w[bb], v[i], row[i]);
+    for (int i = 0; i < CW; ++i) row[i] = fmaf(w[1], v[i], row[i]);
+    Elem<T>::unpack(nb.a, v);
+#pragma unroll
+    for (int i = 0; i < CW; ++i) row[i] = fmaf(w[2], v[i], row[i]);
+    Elem<T>::unpack(nb.b, v);
+#pragma unroll
+    for (int i = 0; i < CW; ++i) row[i] = fmaf(w[3], v[i], row[i]);
+  };
+  for (int m = 0; m <= R; ++m) {
+    const int y0 = 2 * (yo0 + m) - 1, y1 = y0 + 1;
+    const bool v0 = y0 >= 0, v1 = y1 < Hi;          // (y0 < Hi and y1 >= 0 always hold)
+    const uint4* p0 = col + static_cast<ptrdiff_t>(y0) * (Wi + 2);
+    const uint4* p1 = p0 + (Wi + 2);
+    U256 o0, o1, n0, n1;
+    if (v0) o0 = ldg256(p0);
+    if (v1) o1 = ldg256(p1);
+    if (lane == 31) {
+      if (v0) n0 = ldg256(p0 + 2);
+      if (v1) n1 = ldg256(p1 + 2);
+    }
+    if (v0) {
+      const uint4 sa = shfl_down1(o0.a), sb = shfl_down1(o0.b);
+      if (lane != 31) { n0.a = sa; n0.b = sb; }
+      float row[CW];
+      hfilter(o0, n0, row);
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        prev[i] = fmaf(w[2], row[i], prev[i]);
+        cur[i] = fmaf(w[0], row[i], cur[i]);
+      }
+    }
+    if (v1) {
+      const uint4 sa = shfl_down1(o1.a), sb = shfl_down1(o1.b);
+      if (lane != 31) { n1.a = sa; n1.b = sb; }
+      float row[CW];
+      hfilter(o1, n1, row);
+#pragma unroll
+      for (int i = 0; i < CW; ++i) {
+        prev[i] = fmaf(w[3], row[i], prev[i]);
+        cur[i] = fmaf(w[1], row[i], cur[i]);
+      }
+    }
+    if (m > 0) {
+      const uint4 pk = Elem<T>::pack(prev);
+      const size_t idx = out0 + static_cast<size_t>(yo0 + m - 1) * (Wo + 2);
+      dst[idx] = pk;
+      if (xo == 0) dst[idx + Wo] = pk;
+      if (xo == Wo - 1) dst[idx - Wo] = pk;
+#pragma unroll
+      for (int i = 0; i < CW; ++i) { s1 += prev[i]; s2 += prev[i] * prev[i]; }
     }
 #pragma unroll
-    for (int i = 0; i < CW; ++i) acc[i] = fmaf(w[a], row[i], acc[i]);
+    for (int i = 0; i < CW; ++i) { prev[i] = cur[i]; cur[i] = 0.f; }
   }
-  const uint4 pk = Elem<T>::pack(acc);
-  const size_t idx = pt_index(b, planes, pl, Ho, Wo + 2, yo, xo + 1);
-  dst[idx] = pk;
-  if (xo == 0) dst[idx + Wo] = pk;
-  if (xo == Wo - 1) dst[idx - Wo] = pk;
   if (stats != nullptr) {
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < CW; ++i) { s1 += acc[i]; s2 += acc[i] * acc[i]; }
     __shared__ float red[2][4];
     s1 = warp_sum(s1); s2 = warp_sum(s2);
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
@@ -350,71 +421,103 @@ __global__ void __launch_bounds__(128) down2_kernel(const uint4* __restrict__ sr
   }
 }
 
+static int resample_rows_per_block(int rows) { return rows % 4 == 0 ? 4 : (rows % 2 == 0 ? 2 : 1); }
+
 int down2_stat_slots(int dtype, const PT& dst) {
   const int ppu = dst.C / kNU / dtype_cw(dtype);
-  return ppu * dst.H * (dst.W / 128);
+  return ppu * (dst.H / resample_rows_per_block(dst.H)) * (dst.W / 128);
 }
 
 cudaError_t down2_launch(int dtype, PT src, PT dst, cudaStream_t s) {
   const int cw = dtype_cw(dtype);
   if (dst.W % 128 != 0) return cudaErrorInvalidValue;
-  dim3 grid(dst.H * (dst.W / 128), dst.C / cw, dst.B);
+  const int R = resample_rows_per_block(dst.H);
+  dim3 grid((dst.H / R) * (dst.W / 128), dst.C / cw, dst.B);
   const int ppu = dst.C / kNU / cw;
   if (dtype == kBF16)
     return launch_pdl(down2_kernel<__nv_bfloat16>, grid, dim3(128), 0, s, static_cast<const uint4*>(src.ptr),
-                      static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W, dst.stats, dst.slots, ppu);
+                      static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W, dst.stats, dst.slots, ppu, R);
   return launch_pdl(down2_kernel<float>, grid, dim3(128), 0, s, static_cast<const uint4*>(src.ptr),
-                    static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W, dst.stats, dst.slots, ppu);
+                    static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W, dst.stats, dst.slots, ppu, R);
 }
 
 // ops.Resample(up=2) in closed form (separable): y[2i] = (x[i-1] + 3x[i])/4, y[2i+1] = (3x[i] + x[i+1])/4.
+// Thread j owns the padded input unit j (= pixel j-1; pixel j comes from the next lane) and the 32-byte-aligned
+// padded output pair (2j, 2j+1) = pixels 2j-1, 2j, which depend on exactly those two input columns; threads
+// j = 0 .. Wi therefore also produce both wrap-halo columns.  A block walks R input rows and stores 2R output rows.
 template <typename T>
 __global__ void __launch_bounds__(128) up2_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int planes,
-                                                  int Hi, int Wi) {
+                                                  int Hi, int Wi, int R) {
   pdl_launch_dependents();   // PDL: let the next kernel become resident; wait for the previous one's results
   pdl_wait();
   constexpr int CW = Elem<T>::CW;
   const int Ho = Hi * 2, Wo = Wi * 2;
-  const int xsegs = Wo / 128;
-  const int xo = (blockIdx.x % xsegs) * 128 + threadIdx.x, yo = blockIdx.x / xsegs;
+  const int xsegs = Wi / blockDim.x;
+  const int j = (blockIdx.x % xsegs) * blockDim.x + threadIdx.x, i0 = (blockIdx.x / xsegs) * R;
   const int pl = blockIdx.y, b = blockIdx.z;
-  const int xi = xo >> 1, yi = yo >> 1;
-  const int xn = (xo & 1) ? xi + 1 : xi - 1;   // the second horizontal tap (weight 1/4)
-  const int yn = (yo & 1) ? yi + 1 : yi - 1;
-  float acc[CW];
+  const int lane = threadIdx.x & 31;
+  const bool last = j == Wi - 1;      // this thread also produces the pair of column j + 1 = Wi (pixels Wo-1, halo)
+  const uint4* col = src + pt_index(b, planes, pl, Hi, Wi + 2, 0, j);
+  uint4* out = dst + pt_index(b, planes, pl, Ho, Wo + 2, 0, 2 * j);
+  // one output pair from (near row A, far row B) x (left column l = pixel j-1, right column r = pixel j), in the FMA
+  // order of round 1: near row first, and within a row the nearer column first
+  auto emit = [&](uint4* o, const uint4& Alr, const uint4& Arr, const uint4& Blr, const uint4& Brr, bool hasB) {
+    float Al[CW], Ar[CW], Bl[CW], Br[CW];
+    Elem<T>::unpack(Alr, Al); Elem<T>::unpack(Arr, Ar); Elem<T>::unpack(Blr, Bl); Elem<T>::unpack(Brr, Br);
+    float lo[CW], hi[CW];   // pixels 2j-1 (nearer to l) and 2j (nearer to r)
 #pragma unroll
-  for (int i = 0; i < CW; ++i) acc[i] = 0.f;
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    const int yy = a == 0 ? yi : yn;
-    const float wy = a == 0 ? 0.75f : 0.25f;
-    if (yy < 0 || yy >= Hi) continue;
-#pragma unroll
-    for (int bb = 0; bb < 2; ++bb) {
-      const int xx = bb == 0 ? xi : xn;
-      const float wgt = wy * (bb == 0 ? 0.75f : 0.25f);
-      float v[CW];
-      Elem<T>::unpack(src[pt_index(b, planes, pl, Hi, Wi + 2, yy, xx + 1)], v);  // halo handles -1 / Wi
-#pragma unroll
-      for (int i = 0; i < CW; ++i) acc[i] = fmaf(wgt, v[i], acc[i]);
+    for (int c = 0; c < CW; ++c) {
+      float x = fmaf(0.5625f, Al[c], 0.f), y = fmaf(0.5625f, Ar[c], 0.f);
+      x = fmaf(0.1875f, Ar[c], x); y = fmaf(0.1875f, Al[c], y);
+      if (hasB) {
+        x = fmaf(0.1875f, Bl[c], x); y = fmaf(0.1875f, Br[c], y);
+        x = fmaf(0.0625f, Br[c], x); y = fmaf(0.0625f, Bl[c], y);
+      }
+      lo[c] = x; hi[c] = y;
     }
+    stg256(o, Elem<T>::pack_mma(lo), Elem<T>::pack_mma(hi));
+  };
+  // previous / current input row as raw units: left, right, (last thread only) the column after
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  uint4 Pl = zero, Pr = zero, Px = zero, Cl = zero, Cr = zero, Cx = zero;
+  bool hasP = false;
+  auto load_row = [&](int i, uint4& l, uint4& r, uint4& x) {
+    const uint4* p = col + static_cast<size_t>(i) * (Wi + 2);
+    l = *p;
+    r = shfl_down1(l);
+    if (lane == 31) r = p[1];
+    if (last) x = p[2];
+  };
+  if (i0 > 0) { load_row(i0 - 1, Pl, Pr, Px); hasP = true; }
+  for (int i = i0; i <= i0 + R; ++i) {
+    const bool hasC = i < Hi;
+    if (hasC) load_row(i, Cl, Cr, Cx);
+    if (i > i0) {            // odd output row 2i-1 of input row i-1: near = previous row, far = current row
+      uint4* o = out + static_cast<size_t>(2 * i - 1) * (Wo + 2);
+      emit(o, Pl, Pr, Cl, Cr, hasC);
+      if (last) emit(o + 2, Pr, Px, Cr, Cx, hasC);
+    }
+    if (i < i0 + R) {        // even output row 2i of input row i: near = current row, far = previous row
+      uint4* o = out + static_cast<size_t>(2 * i) * (Wo + 2);
+      emit(o, Cl, Cr, Pl, Pr, hasP);
+      if (last) emit(o + 2, Cr, Cx, Pr, Px, hasP);
+    }
+    Pl = Cl; Pr = Cr; Px = Cx;
+    hasP = true;
   }
-  const uint4 pk = Elem<T>::pack_mma(acc);
-  const size_t idx = pt_index(b, planes, pl, Ho, Wo + 2, yo, xo + 1);
-  dst[idx] = pk;
-  if (xo == 0) dst[idx + Wo] = pk;
-  if (xo == Wo - 1) dst[idx - Wo] = pk;
 }
 
 cudaError_t up2_launch(int dtype, PT src, PT dst, cudaStream_t s) {
   const int cw = dtype_cw(dtype);
   if (dst.W % 128 != 0) return cudaErrorInvalidValue;
-  dim3 grid(dst.H * (dst.W / 128), dst.C / cw, dst.B);
+  const int R = resample_rows_per_block(src.H);
+  const int threads = src.W % 128 == 0 ? 128 : 64;   // dst.W % 128 == 0 guarantees src.W % 64 == 0
+  dim3 grid((src.H / R) * (src.W / threads), dst.C / cw, dst.B);
   if (dtype == kBF16)
-    return launch_pdl(up2_kernel<__nv_bfloat16>, grid, dim3(128), 0, s, static_cast<const uint4*>(src.ptr),
-                      static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W);
-  return launch_pdl(up2_kernel<float>, grid, dim3(128), 0, s, static_cast<const uint4*>(src.ptr),
-                    static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W);
+    return launch_pdl(up2_kernel<__nv_bfloat16>, grid, dim3(threads), 0, s, static_cast<const uint4*>(src.ptr),
+                      static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W, R);
+  return launch_pdl(up2_kernel<float>, grid, dim3(threads), 0, s, static_cast<const uint4*>(src.ptr),
+                    static_cast<uint4*>(dst.ptr), dst.C / cw, src.H, src.W, R);
 }
 
 // =============================================================================== conditioning

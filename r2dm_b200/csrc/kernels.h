@@ -70,6 +70,7 @@ struct ConvLaunch {
   ConvXform xf;       // fused input normalisation (enabled = 0: plain convolution)
   unsigned long long* ktime;  // developer: device [2] receiving (first CTA start, last CTA end), globaltimer ns
   int reverse;        // tile order back to front (alternated between consecutive launches, see conv_umma.cu)
+  int round_out;      // fp32 engine: store the output rounded to nearest tf32 (its only consumer is a tensor-core operand)
   CUtensorMap tmap0, tmap1, tmap2, tmap3;
 };
 // Fills l.tmap0/tmap1 for the current in0/in1 pointers.  Returns 0 on success.
@@ -142,8 +143,10 @@ cudaError_t up2_launch(int dtype, PT src, PT dst, cudaStream_t s);
 // qkv: planar-16 tensor with 3E channels ([q;k;v]); out: E channels. softmax(q k^T / sqrt(hd)) v
 cudaError_t attention_launch(int dtype, PT qkv, PT out, int heads, cudaStream_t s);   // exact fp32 FMA-pipe version
 // bf16 tensor-core version (tcgen05): needs a TMA map of the qkv tensor
-int attention_make_tmap(CUtensorMap* tm, const PT& qkv, int heads);
-cudaError_t attention_umma_launch(PT qkv, PT out, int heads, const CUtensorMap& tm, cudaStream_t s);
+int attention_key_tile(int dtype);   // keys per tile of the tensor-core kernel (128 bf16 / 64 tf32)
+int attention_make_tmaps(CUtensorMap* tm_q, CUtensorMap* tm_kv, int dtype, const PT& qkv, int heads);
+cudaError_t attention_umma_launch(int dtype, PT qkv, PT out, int heads, const CUtensorMap& tm_q,
+                                  const CUtensorMap& tm_kv, cudaStream_t s);
 
 // ------------------------------------------------------------------ conditioning table
 struct CondEmbed {

@@ -65,7 +65,8 @@ struct Op {
   int gn_gamma = -1;      // raw index of gamma (beta = +1), or -1 for AdaGN
   bool is_output = false; // network output conv (writes pred NCHW)
   bool xf_film = false;   // conv with fused AdaGN: film pointers patched per forward
-  CUtensorMap attn_tmap;  // ATTN (bf16): TMA map of the packed qkv tensor
+  CUtensorMap attn_tmap, attn_tmap_kv;  // ATTN: TMA maps of the packed qkv tensor (Q tile / K, V tiles)
+  bool attn_exact = false;              // fp32 engine with option attn_exact: FMA-pipe kernel instead of kind::tf32
 };
 
 }  // namespace
@@ -113,7 +114,7 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
 namespace r2dm {
 // Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
 static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
-static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip"};
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact"};
 int get_option(const char* name, int dflt) {
   auto& m = option_map();
   auto it = m.find(name);
@@ -420,6 +421,7 @@ struct Builder {
       if (b.attn) {
         const std::string p = b.name + ".self_attn_block";
         const int qkv = conv(p + ".attn.in_proj", h, -1, -1, 1.f, false, false, 3, m->raw_by_name.at(p + ".norm.weight"));
+        prog.back().conv.round_out = 1;   // q, k, v are only ever read as tensor-core operands (fp32 engine: tf32)
         const int att = pl.new_tensor(b.cout, T(h).H, T(h).W, 0);
         {
           Op op; op.kind = Op::ATTN; op.a = T(qkv); op.b = T(att); op.heads = c.attn_num_heads;
@@ -659,8 +661,9 @@ int r2dm_bind_workspace(r2dm_handle h, void* workspace, size_t bytes, int batch,
         op.conv.xf.gamma = h->raw_ptr(op.gn_gamma);
         op.conv.xf.beta = h->raw_ptr(op.gn_gamma + 1);
       }
-    } else if (op.kind == Op::ATTN && h->dtype == kBF16) {
-      int rc = attention_make_tmap(&op.attn_tmap, op.a, op.heads);
+    } else if (op.kind == Op::ATTN) {
+      op.attn_exact = h->dtype != kBF16 && get_option("attn_exact", 0) != 0;
+      int rc = op.attn_exact ? 0 : attention_make_tmaps(&op.attn_tmap, &op.attn_tmap_kv, h->dtype, op.a, op.heads);
       if (rc) return fail(-4, "cuTensorMapEncodeTiled failed for attention (%d)", rc);
     } else if (op.kind == Op::GN && op.gn_gamma >= 0) {
       op.gn.gamma = h->raw_ptr(op.gn_gamma);
@@ -727,7 +730,8 @@ static int launch_op(r2dm_handle h, Op& op, const float* x, const float* film, c
     case Op::DOWN: CUDA_TRY(down2_launch(h->dtype, op.a, op.b, s)); break;
     case Op::UP: CUDA_TRY(up2_launch(h->dtype, op.a, op.b, s)); break;
     case Op::ATTN:
-      if (h->dtype == kBF16) CUDA_TRY(attention_umma_launch(op.a, op.b, op.heads, op.attn_tmap, s));
+      if (!op.attn_exact)
+        CUDA_TRY(attention_umma_launch(h->dtype, op.a, op.b, op.heads, op.attn_tmap, op.attn_tmap_kv, s));
       else CUDA_TRY(attention_launch(h->dtype, op.a, op.b, op.heads, s));
       break;
   }
@@ -1162,11 +1166,11 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
   PT out = make_pt(sc, dtype, B, E, H, W, 0);
   if (!in.ptr || !out.ptr) return fail(-1, "scratch too small");
   CUDA_TRY(pack_nchw(dtype, qkv, B, 3 * E, H, W, in, 0, s));
-  if (dtype == kBF16) {
-    CUtensorMap tm;
-    int rc = attention_make_tmap(&tm, in, heads);
+  if (dtype == kBF16 || get_option("attn_exact", 0) == 0) {
+    CUtensorMap tm, tm_kv;
+    int rc = attention_make_tmaps(&tm, &tm_kv, dtype, in, heads);
     if (rc) return fail(-4, "tensor map encode failed (%d)", rc);
-    CUDA_TRY(attention_umma_launch(in, out, heads, tm, s));
+    CUDA_TRY(attention_umma_launch(dtype, in, out, heads, tm, tm_kv, s));
   } else {
     CUDA_TRY(attention_launch(dtype, in, out, heads, s));
   }

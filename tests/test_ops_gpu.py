@@ -129,6 +129,32 @@ def test_attention_core(case, dtype):
     _check(y, ref, dtype, f"attention {case}", tf32_out=True)
 
 
+def test_attention_exact_option():
+    """fp32 engine: `attn_exact` swaps the kind::tf32 tensor-core attention for the fp32 FMA kernel (no operand
+    rounding at all: unrounded inputs, 2e-5 before the tf32-rounded store)."""
+    from r2dm_b200 import _lib as L
+    from r2dm_b200 import ops
+    B, E, heads, H, W = 1, 256, 8, 2, 128
+    hd = E // heads
+    g = torch.Generator().manual_seed(10)
+    qkv = torch.randn(B, 3 * E, H, W, generator=g)
+    tok = qkv.flatten(2).transpose(1, 2)
+    q, k, v = [t.reshape(B, -1, heads, hd).transpose(1, 2) for t in tok.split(E, dim=-1)]
+    att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    ref = (att @ v).transpose(1, 2).reshape(B, -1, E).transpose(1, 2).reshape(B, E, H, W)
+    L.check(L.lib().r2dm_set_option(b"attn_exact", 1))
+    try:
+        y_exact = ops.attention_core(qkv.cuda(), heads, dtype="fp32")
+    finally:
+        L.check(L.lib().r2dm_set_option(b"attn_exact", 0))
+    y_tf32 = ops.attention_core(qkv.cuda(), heads, dtype="fp32")
+    torch.cuda.synchronize()
+    e_exact, e_tf32 = rel_l2(y_exact, ref), rel_l2(y_tf32, ref)
+    assert e_exact <= 5e-4, e_exact
+    assert e_tf32 <= 2e-3, e_tf32          # unrounded q / k / v: the tensor core truncates them to tf32
+    assert not torch.equal(y_exact, y_tf32)
+
+
 @pytest.mark.parametrize("dtype", ["bf16", "fp32"])
 @pytest.mark.parametrize("case", [(2, 64, 64, 8, 256, 3, False), (1, 128, 64, 4, 128, 3, True),
                                   (2, 256, 128, 2, 128, 3, True), (1, 512, 1536, 4, 128, 1, False),
