@@ -169,6 +169,20 @@ int r2dm_surface_normal(const float* points, float* out, int batch, int H, int W
 int r2dm_bev_histogram(const float* points, const float* edges, unsigned int* counts, float* hist, int batch,
                        int num_points, int bins, float min_depth, float max_depth, void* stream);
 
+/* metrics/extractor/pointnet.py:61-81 PointNet1.forward (the FPD feature extractor of evaluate.py): points
+ * [B][3][N] (N a multiple of 128; the 64 x 1024 range image flattened) -> features [B][1024 + 512 + 256 + k].
+ * The point-wise layers run as 1x1 tensor-core convolutions with the global max pool fused into the last one.
+ * Weights are fp32 device pointers with BatchNorm (eval) folded in, in the order stn.conv1-3, stn.fc1-3 (the
+ * identity of pointnet.py:32 added to the last bias), feat.conv1-3, fc1-3; weight[i] is [out][in] row-major. */
+typedef struct {
+  const float* weight[12];
+  const float* bias[12];
+  int num_classes; /* k of the classifier head (16 for the ShapeNet checkpoint the reference downloads) */
+} r2dm_pointnet_weights;
+size_t r2dm_pointnet_scratch_bytes(int dtype, int batch, int num_points);
+int r2dm_pointnet_features(int dtype, const float* points, const r2dm_pointnet_weights* w, float* features,
+                           int batch, int num_points, void* scratch, size_t scratch_bytes, void* stream);
+
 /* --- single-operator entry points (used by the parity tests; same kernels as the network) ----------
  * All take fp32 NCHW tensors and a scratch buffer for the packed intermediates. */
 size_t r2dm_op_scratch_bytes(int batch, int max_channels, int H, int W);

@@ -143,3 +143,66 @@ def point_cloud_to_histogram(pc: Tensor, field_size: float = 160.0, bins: int = 
     hist = torch.zeros(bins * bins, dtype=pc.dtype)
     hist.index_add_(0, pos[:, 0] * bins + pos[:, 1], torch.ones(pos.shape[0], dtype=pc.dtype))
     return hist.view(bins, bins)
+
+
+# --------------------------------------------------------------------------------------- PointNet features
+def random_pointnet_state_dict(seed: int, k: int = 16):
+    """Seeded synthetic weights with the key set of the reference's PointNet1 (metrics/extractor/pointnet.py:67-81;
+    the pretrained SpareNet checkpoint is not available offline): default-init-like weights, BatchNorm affine and
+    running statistics drawn away from (1, 0, 0, 1) so that the BatchNorm folding is exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def layer(name, cout, cin, conv):
+        bound = 1.0 / cin ** 0.5
+        shape = (cout, cin, 1) if conv else (cout, cin)
+        sd[name + ".weight"] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+
+    def bn(name, c):
+        sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".bias"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(1)
+
+    for pre in ("feat.stn.", "feat."):
+        layer(pre + "conv1", 64, 3, True); layer(pre + "conv2", 128, 64, True); layer(pre + "conv3", 1024, 128, True)
+        bn(pre + "bn1", 64); bn(pre + "bn2", 128); bn(pre + "bn3", 1024)
+    layer("feat.stn.fc1", 512, 1024, False); layer("feat.stn.fc2", 256, 512, False); layer("feat.stn.fc3", 9, 256, False)
+    bn("feat.stn.bn4", 512); bn("feat.stn.bn5", 256)
+    layer("fc1", 512, 1024, False); layer("fc2", 256, 512, False); layer("fc3", k, 256, False)
+    bn("bn1", 512); bn("bn2", 256)
+    return sd
+
+
+def pointnet_features(sd, x: Tensor) -> Tensor:
+    """PointNet1.forward in eval mode (metrics/extractor/pointnet.py:22-33, 47-58, 74-81) as plain matrix algebra:
+    x [B,3,N] -> cat(global feature [1024], fc1 [512], fc2 [256], logits [k])."""
+    def bn(h, name, eps=1e-5):
+        shape = (1, -1, 1) if h.dim() == 3 else (1, -1)
+        m, v = sd[name + ".running_mean"].view(shape), sd[name + ".running_var"].view(shape)
+        return (h - m) / torch.sqrt(v + eps) * sd[name + ".weight"].view(shape) + sd[name + ".bias"].view(shape)
+
+    def pw(h, name):     # Conv1d with kernel size 1
+        return torch.einsum("oc,bcn->bon", sd[name + ".weight"][:, :, 0], h) + sd[name + ".bias"].view(1, -1, 1)
+
+    def fc(h, name):
+        return h @ sd[name + ".weight"].t() + sd[name + ".bias"]
+
+    def trunk(h, pre, relu_last):
+        h = torch.relu(bn(pw(h, pre + "conv1"), pre + "bn1"))
+        h = torch.relu(bn(pw(h, pre + "conv2"), pre + "bn2"))
+        h = bn(pw(h, pre + "conv3"), pre + "bn3")
+        return (torch.relu(h) if relu_last else h).amax(dim=2)
+
+    g = trunk(x, "feat.stn.", True)
+    g = torch.relu(bn(fc(g, "feat.stn.fc1"), "feat.stn.bn4"))
+    g = torch.relu(bn(fc(g, "feat.stn.fc2"), "feat.stn.bn5"))
+    trans = fc(g, "feat.stn.fc3").view(-1, 3, 3) + torch.eye(3)
+    moved = torch.bmm(x.transpose(2, 1), trans).transpose(2, 1)
+    x1 = trunk(moved, "feat.", False)
+    x2 = torch.relu(bn(fc(x1, "fc1"), "bn1"))
+    x3 = torch.relu(bn(fc(x2, "fc2"), "bn2"))
+    x4 = fc(x3, "fc3")
+    return torch.cat((x1, x2, x3, x4), dim=1)

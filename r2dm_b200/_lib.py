@@ -44,6 +44,11 @@ class R2dmPhilox(C.Structure):
     ]
 
 
+class R2dmPointNetWeights(C.Structure):
+    """r2dm_pointnet_weights (include/r2dm_b200.h): BatchNorm-folded fp32 device pointers."""
+    _fields_ = [("weight", C.c_void_p * 12), ("bias", C.c_void_p * 12), ("num_classes", C.c_int)]
+
+
 class R2dmError(RuntimeError):
     pass
 
@@ -85,6 +90,9 @@ _SIGS = {
     "r2dm_bilinear_rasterize": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "r2dm_surface_normal": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "r2dm_bev_histogram": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
+    "r2dm_pointnet_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "r2dm_pointnet_features": (C.c_int, [C.c_int, _P, C.POINTER(R2dmPointNetWeights), _P, C.c_int, C.c_int, _P,
+                                         C.c_size_t, _P]),
     "r2dm_op_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "r2dm_op_conv": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_float, _P, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),

@@ -65,6 +65,8 @@ struct ConvParams {
   int coef_ch, coef_bytes;        // transform coefficient table at the start of dynamic smem: 2 x coef_ch floats
   int reverse;                    // walk the tiles back to front
   int round_out;                  // fp32: round the stored output to nearest tf32
+  int relu;                       // 1x1 only: max(0, .) after bias / scale
+  float* colmax;                  // 1x1 only: [B][cout_pad] running maximum over pixels, or null
   int debug;  // developer ablation knob (R2DM_CONV_DEBUG): 1 no epilogue stores, 2 no MMA issue, 4 no TMA
   unsigned long long* ktime;  // developer: [2] = (min CTA start, max CTA end) in globaltimer ns, or null
   unsigned long long* trace;  // developer timeline (r2dm_debug_set_trace): [5 roles][cap] clock64 of CTA 0

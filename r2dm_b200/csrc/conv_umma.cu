@@ -552,6 +552,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
         for (int u = 0; u < NSUB; ++u) { s1p[u] = pack2(0.f, 0.f); s2p[u] = pack2(0.f, 0.f); }
         const f32x2 scale2 = pack2(p.scale, p.scale);
+        // 1x1 launches: per-channel maximum over this thread's pixels (point-wise MLP + global max pool)
+        float cm[TAPS == 1 ? CB : 1];
+        if constexpr (TAPS == 1) {
+#pragma unroll
+          for (int i = 0; i < CB; ++i) cm[i] = -INFINITY;
+        }
 #pragma unroll
         for (int r = r_begin; r < HT; r += RSTEP) {
           const int y = y0 + r;
@@ -600,11 +606,26 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                   for (int i = 0; i < PPU; ++i) o2[i] = fma2(r2[i], scale2, o2[i]);
                 }
+                if constexpr (TAPS == 1) {
+                  if (p.relu | (p.colmax != nullptr)) {
+#pragma unroll
+                    for (int i = 0; i < PPU; ++i) {
+                      float lo, hi;
+                      unpack2(o2[i], lo, hi);
+                      if (p.relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); o2[i] = pack2(lo, hi); }
+                      cm[u * CW + 2 * i] = fmaxf(cm[u * CW + 2 * i], lo);
+                      cm[u * CW + 2 * i + 1] = fmaxf(cm[u * CW + 2 * i + 1], hi);
+                    }
+                  }
+                }
                 const int sub = (u * CW) / 8;
 #pragma unroll
                 for (int i = 0; i < PPU; ++i) {
                   s1p[sub] = add2(s1p[sub], o2[i]);
                   s2p[sub] = fma2(o2[i], o2[i], s2p[sub]);
+                }
+                if constexpr (TAPS == 1) {
+                  if (out == nullptr) continue;      // max-pool only: the tensor itself is not needed
                 }
                 uint4 pk = Elem<T>::pack2x(o2);
                 if (sizeof(T) == 4 && p.round_out) {
@@ -617,6 +638,30 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 if (seam) out[static_cast<int>(idx) + seam_off] = pk;
               }
             }
+          }
+        }
+        if constexpr (TAPS == 1 && !NCHW) {
+          if (p.colmax != nullptr) {
+            // transposing butterfly: afterwards lane i holds the warp maximum of channel c0 + i (CB = 32) -
+            // 31 shuffles instead of 5 per channel
+            static_assert(CB == 32, "column maximum assumes 32-channel chunks");
+#pragma unroll
+            for (int rd = 0; rd < 5; ++rd) {
+              const int nv = 32 >> rd, off = 16 >> rd;
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < nv / 2; ++i) {
+                const float send = upper ? cm[i] : cm[i + nv / 2];
+                const float keep = upper ? cm[i + nv / 2] : cm[i];
+                cm[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+              }
+            }
+            float* dst = p.colmax + static_cast<size_t>(b) * p.cout_pad + n0 + c0 + lane;
+            const float v = cm[0];
+            // float maximum with integer atomics: non-negative values order like ints, negative ones like
+            // reversed unsigned ints; the buffer starts at -inf
+            if (v >= 0.f) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(v));
+            else atomicMin(reinterpret_cast<unsigned int*>(dst), __float_as_uint(v));
           }
         }
         float ssum[NSUB][2];
@@ -863,6 +908,8 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.coef_bytes = 2 * p.coef_ch * static_cast<int>(sizeof(float));
   p.reverse = l.reverse;
   p.round_out = l.round_out;
+  p.relu = l.relu; p.colmax = l.colmax;
+  if ((l.relu || l.colmax) && TAPS != 1) return cudaErrorInvalidConfiguration;
   p.ktime = l.ktime;
   const int avail = kSmemBudget - 256 - p.coef_bytes - (p.wres ? static_cast<int>(wbytes) : 0);
   int stages = avail / p.stage_bytes;
@@ -890,6 +937,13 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
     if (cap > 0 && grid > cap) grid = cap;
   }
   if (grid > p.tiles_total) grid = p.tiles_total;
+  if (get_option("compact_grid", 0)) {
+    // experiment (measured: no gain, 2.43 vs 2.42 ms per forward): the launch ends with the CTAs that own
+    // ceil(tiles / grid) tiles, so ceil(tiles / that) CTAs give the same critical path (512 tiles: 128 x 4 instead
+    // of 68 x 4 + 80 x 3) and the idle SMs would return their share of the power budget
+    const int per = (p.tiles_total + grid - 1) / grid;
+    grid = (p.tiles_total + per - 1) / per;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];

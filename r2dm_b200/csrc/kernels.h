@@ -71,6 +71,11 @@ struct ConvLaunch {
   unsigned long long* ktime;  // developer: device [2] receiving (first CTA start, last CTA end), globaltimer ns
   int reverse;        // tile order back to front (alternated between consecutive launches, see conv_umma.cu)
   int round_out;      // fp32 engine: store the output rounded to nearest tf32 (its only consumer is a tensor-core operand)
+  // 1x1 launches only (point-wise MLPs over the range image, pointnet.cu): ReLU after bias / scale, and a running
+  // per-(image, channel) maximum over all pixels into colmax [B][cout_pad] (float bits, initialised to -inf);
+  // with colmax set and out.ptr == nullptr the output tensor itself is not stored
+  int relu;
+  float* colmax;
   CUtensorMap tmap0, tmap1, tmap2, tmap3;
 };
 // Fills l.tmap0/tmap1 for the current in0/in1 pointers.  Returns 0 on success.
@@ -204,6 +209,11 @@ cudaError_t lidar_postprocess_launch(const float* sample, const float* angles, f
                                      int H, int W, int depth_format, float min_depth,
                                      float max_depth, cudaStream_t s);
 
+// PointNet feature extractor helpers (pointnet.cu; metrics/extractor/pointnet.py)
+cudaError_t fill_launch(float* p, float v, size_t n, cudaStream_t s);
+cudaError_t dense_launch(const float* in, int in_stride, const float* w, const float* bias, float* out, int out_stride,
+                         int B, int K, int N, int relu, cudaStream_t s);
+cudaError_t point_transform_launch(const float* x, const float* trans, float* y, int B, int N, cudaStream_t s);
 // caller-side consumers of the generated point clouds (render.cu; utils/render.py, metrics/bev.py)
 cudaError_t render_splat_launch(const float* points, const float* colors, const float* R, const float* t,
                                 float* acc, float* out, int B, int N, int size, float focal, cudaStream_t s);

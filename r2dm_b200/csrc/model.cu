@@ -114,7 +114,7 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
 namespace r2dm {
 // Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
 static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
-static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact"};
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid"};
 int get_option(const char* name, int dflt) {
   auto& m = option_map();
   auto it = m.find(name);
@@ -1175,6 +1175,115 @@ int r2dm_op_attention(int dtype, const float* qkv, float* y, int B, int E, int h
     CUDA_TRY(attention_launch(dtype, in, out, heads, s));
   }
   CUDA_TRY(unpack_nchw(dtype, out, y, 0, E, s));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- PointNet features
+namespace {
+int pointnet_image_width(int N) {
+  for (int w : {1024, 512, 256, 128})
+    if (N % w == 0) return w;
+  return 0;
+}
+// one point-wise layer (Conv1d k=1 with folded BatchNorm) as a 1x1 convolution over the [H x W] point image
+int pointwise_layer(int dtype, Scratch& sc, const PT& in, int cin, int cout, const float* w, const float* b, int relu,
+                    PT* out, float* colmax, cudaStream_t s) {
+  ConvLaunch l;
+  memset(&l, 0, sizeof(l));
+  l.dtype = dtype; l.taps = 1;
+  l.nt = pick_nt(cout);
+  l.cin_pad = round_up(cin, conv_stage_channels(dtype, 1));
+  if (in.C != l.cin_pad) return fail(-1, "pointnet: layer input has %d channel planes, expected %d", in.C, l.cin_pad);
+  l.cout = cout; l.cout_pad = round_up(cout, l.nt);
+  l.ht = in.H >= 2 ? 2 : 1;
+  l.in0 = in;
+  if (out != nullptr) {
+    // the consumer reads whole K stages: the padded width must already be a multiple of the stage K
+    if (l.cout_pad % conv_stage_channels(dtype, 1)) return fail(-1, "pointnet: layer width %d not a stage multiple", l.cout_pad);
+    *out = make_pt(sc, dtype, in.B, l.cout_pad, in.H, in.W, 0);
+    if (!out->ptr) return fail(-1, "pointnet: scratch too small");
+    l.out = *out;
+  } else {
+    l.out.B = in.B; l.out.C = l.cout_pad; l.out.H = in.H; l.out.W = in.W;   // dimensions only: nothing is stored
+  }
+  void* wp = sc.take(conv_packed_weight_bytes(dtype, 1, l.nt, l.cin_pad, l.cout_pad));
+  float* bp = static_cast<float*>(sc.take(static_cast<size_t>(l.cout_pad) * 4));
+  if (!wp || !bp) return fail(-1, "pointnet: scratch too small");
+  CUDA_TRY(pack_conv_weight(dtype, 1, l.nt, w, cout, cin, l.cin_pad, l.cout_pad, wp, s));
+  CUDA_TRY(cudaMemsetAsync(bp, 0, static_cast<size_t>(l.cout_pad) * 4, s));
+  CUDA_TRY(cudaMemcpyAsync(bp, b, static_cast<size_t>(cout) * 4, cudaMemcpyDeviceToDevice, s));
+  l.wpacked = wp; l.bias = bp; l.scale = 1.f;
+  l.relu = relu; l.colmax = colmax;
+  int rc = conv_make_tmaps(l);
+  if (rc) return fail(-4, "tensor map encode failed (%d)", rc);
+  CUDA_TRY(conv_launch(l, s));
+  return 0;
+}
+}  // namespace
+
+size_t r2dm_pointnet_scratch_bytes(int dtype, int batch, int num_points) {
+  const int W = pointnet_image_width(num_points);
+  if (W == 0 || batch < 1) return 0;
+  PT t; t.B = batch; t.H = num_points / W; t.W = W;
+  size_t total = 0;
+  for (int c : {64, 64, 128}) { t.C = round_up(c, conv_stage_channels(dtype, 1)); total += align_up(t.bytes(dtype), 1024); }
+  total *= 2;                                                          // both trunks
+  total += static_cast<size_t>(batch) * 3 * num_points * sizeof(float);   // transformed points
+  total += 8u << 20;                                                   // packed weights, biases, pooled vectors
+  return total;
+}
+
+int r2dm_pointnet_features(int dtype, const float* points, const r2dm_pointnet_weights* w, float* features, int batch,
+                           int num_points, void* scratch, size_t scratch_bytes, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!points || !w || !features || !scratch) return fail(-1, "null argument");
+  if (dtype != kF32 && dtype != kBF16) return fail(-1, "dtype must be R2DM_F32 or R2DM_BF16");
+  const int W = pointnet_image_width(num_points);
+  if (W == 0 || batch < 1) return fail(-1, "num_points must be a multiple of 128");
+  for (int i = 0; i < 12; ++i)
+    if (!w->weight[i] || !w->bias[i]) return fail(-1, "pointnet weight %d missing", i);
+  const int k = w->num_classes;
+  if (k < 1 || k > 4096) return fail(-1, "bad num_classes");
+  const int H = num_points / W, B = batch, FD = 1024 + 512 + 256 + k;
+  Scratch sc{static_cast<uint8_t*>(scratch), scratch_bytes};
+  float* pooled = static_cast<float*>(sc.take(static_cast<size_t>(B) * 1024 * 4));
+  float* v512 = static_cast<float*>(sc.take(static_cast<size_t>(B) * 512 * 4));
+  float* v256 = static_cast<float*>(sc.take(static_cast<size_t>(B) * 256 * 4));
+  float* trans = static_cast<float*>(sc.take(static_cast<size_t>(B) * 9 * 4));
+  float* moved = static_cast<float*>(sc.take(static_cast<size_t>(B) * 3 * num_points * 4));
+  if (!pooled || !v512 || !v256 || !trans || !moved) return fail(-1, "scratch too small");
+  const int cin0 = round_up(3, conv_stage_channels(dtype, 1));
+  // trunk(points, first conv index) -> pooled [B][1024]; relu_last: STN3d applies ReLU before the pool (:26-27),
+  // PointNetfeat does not (:56-57)
+  auto trunk = [&](const float* pts, int wi, int relu_last) -> int {
+    PT in = make_pt(sc, dtype, B, cin0, H, W, 0);
+    if (!in.ptr) return fail(-1, "scratch too small");
+    CUDA_TRY(cudaMemsetAsync(in.ptr, 0, in.bytes(dtype), s));
+    CUDA_TRY(pack_nchw(dtype, pts, B, 3, H, W, in, 0, s));
+    PT h1, h2;
+    int rc = pointwise_layer(dtype, sc, in, 3, 64, w->weight[wi], w->bias[wi], 1, &h1, nullptr, s);
+    if (rc) return rc;
+    rc = pointwise_layer(dtype, sc, h1, 64, 128, w->weight[wi + 1], w->bias[wi + 1], 1, &h2, nullptr, s);
+    if (rc) return rc;
+    CUDA_TRY(fill_launch(pooled, -INFINITY, static_cast<size_t>(B) * 1024, s));
+    return pointwise_layer(dtype, sc, h2, 128, 1024, w->weight[wi + 2], w->bias[wi + 2], relu_last, nullptr, pooled, s);
+  };
+  // STN3d (pointnet.py:22-33)
+  int rc = trunk(points, 0, 1);
+  if (rc) return rc;
+  CUDA_TRY(dense_launch(pooled, 1024, w->weight[3], w->bias[3], v512, 512, B, 1024, 512, 1, s));
+  CUDA_TRY(dense_launch(v512, 512, w->weight[4], w->bias[4], v256, 256, B, 512, 256, 1, s));
+  CUDA_TRY(dense_launch(v256, 256, w->weight[5], w->bias[5], trans, 9, B, 256, 9, 0, s));
+  // PointNetfeat (:47-58) on the transformed points
+  CUDA_TRY(point_transform_launch(points, trans, moved, B, num_points, s));
+  rc = trunk(moved, 6, 0);
+  if (rc) return rc;
+  // PointNet1 head (:74-81): feature = cat(x1, x2, x3, x4)
+  CUDA_TRY(cudaMemcpy2DAsync(features, static_cast<size_t>(FD) * 4, pooled, 1024 * 4, 1024 * 4, B,
+                             cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(dense_launch(pooled, 1024, w->weight[9], w->bias[9], features + 1024, FD, B, 1024, 512, 1, s));
+  CUDA_TRY(dense_launch(features + 1024, FD, w->weight[10], w->bias[10], features + 1536, FD, B, 512, 256, 1, s));
+  CUDA_TRY(dense_launch(features + 1536, FD, w->weight[11], w->bias[11], features + 1792, FD, B, 256, k, 0, s));
   return 0;
 }
 

@@ -200,6 +200,24 @@ def main():
                       small_kw=dict(field_size=40.0, bins=16, min_depth=1.0, max_depth=30.0))
     print(f"  bev histogram ok ({int(hists[0].sum())} / {clouds.shape[1]} points counted)")
 
+    # ---------------------------------------------------------------- PointNet1 features (random weights)
+    from metrics.extractor.pointnet import PointNet1 as RefPointNet1
+    sd = RO.random_pointnet_state_dict(seed=5, k=16)
+    ref_net = RefPointNet1(k=16)
+    ref_net.load_state_dict(sd)
+    ref_net.eval()
+    g = torch.Generator().manual_seed(6)
+    small = torch.randn(3, 3, 2048, generator=g) * 0.5
+    clouds_n = (clouds / 80.0).transpose(1, 2).contiguous()                  # evaluate.py:121: point_clouds / max depth
+    feats = {}
+    for name, pc in (("small", small), ("scene", clouds_n)):
+        ref = ref_net(pc)
+        e = relerr(RO.pointnet_features(sd, pc), ref)
+        print(f"  pointnet {name} {tuple(pc.shape)}: oracle vs reference l2-rel {e:.2e}")
+        assert e < 1e-5
+        feats[name] = ref
+    out["pointnet"] = dict(seed=5, k=16, small=small, feats=feats)
+
     path = os.path.join(HERE, "render.pt")
     torch.save(out, path)
     print(f"wrote {path} ({os.path.getsize(path) / 1e6:.1f} MB)")

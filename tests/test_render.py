@@ -181,3 +181,51 @@ def test_bev_histogram_gpu(fx):
     hb = R.point_clouds_to_histograms(pc.cuda()).cpu()
     for b in range(3):
         assert torch.equal(hb[b], RO.point_cloud_to_histogram(pc[b]))
+
+
+# ------------------------------------------------------------------------------------------- PointNet features
+def test_oracle_pointnet_against_golden(fx):
+    pn = fx["pointnet"]
+    sd = RO.random_pointnet_state_dict(pn["seed"], pn["k"])
+    assert rel_l2(RO.pointnet_features(sd, pn["small"]), pn["feats"]["small"]) < 1e-5
+    clouds = (bev_clouds(fx) / 80.0).transpose(1, 2).contiguous()
+    assert rel_l2(RO.pointnet_features(sd, clouds), pn["feats"]["scene"]) < 1e-5
+
+
+def test_pointnet_module_mirrors_reference_state_dict(fx):
+    """Same module tree / parameter names as metrics/extractor/pointnet.py: a reference state dict loads strictly;
+    no CPU path."""
+    from r2dm_b200 import pointnet as P
+    from r2dm_b200._lib import R2dmError
+    pn = fx["pointnet"]
+    net = P.PointNet1(k=pn["k"])
+    net.load_state_dict(RO.random_pointnet_state_dict(pn["seed"], pn["k"]), strict=True)
+    with pytest.raises(NotImplementedError):
+        net.train()(pn["small"])
+    with pytest.raises(R2dmError):
+        net.eval()(pn["small"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pointnet_features_gpu(fx, precision):
+    """Tolerances: the point-wise layers multiply tf32 / bf16 operands on the tensor cores (inputs and hidden
+    activations rounded to the operand type), three layers deep, followed by a max over up to 65 536 points:
+    l2-rel 3e-3 (tf32) / 3e-2 (bf16) on every feature block."""
+    from r2dm_b200 import pointnet as P
+    pn = fx["pointnet"]
+    net = P.PointNet1(k=pn["k"], precision=precision)
+    net.load_state_dict(RO.random_pointnet_state_dict(pn["seed"], pn["k"]))
+    net = net.eval().cuda()
+    tol = 3e-3 if precision == "fp32" else 3e-2
+    clouds = (bev_clouds(fx) / 80.0).transpose(1, 2).contiguous()
+    for name, pc in (("small", pn["small"]), ("scene", clouds)):
+        y = net(pc.cuda()).cpu()
+        ref = pn["feats"][name]
+        assert y.shape == ref.shape
+        for lo, hi in ((0, 1024), (1024, 1536), (1536, 1792), (1792, 1792 + pn["k"])):
+            e = rel_l2(y[:, lo:hi], ref[:, lo:hi])
+            assert e < tol, (name, precision, lo, e)
+    # batch composition must not matter (per-cloud max pool, per-cloud transform)
+    y2 = net(pn["small"][1:2].cuda()).cpu()
+    assert torch.equal(y2[0], net(pn["small"].cuda()).cpu()[1])
