@@ -86,6 +86,12 @@ class PointNet1(nn.Module):
         self.bn2 = nn.BatchNorm1d(256)
         self.k = k
         self.precision = precision      # "fp32" = tf32 tensor cores, "bf16"
+        self._cache = None              # (parameter versions, device) -> folded weights, scratch
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d["_cache"] = None
+        return d
 
     def _folded(self):
         return (self.feat.stn.folded() + self.feat.folded()
@@ -102,7 +108,11 @@ class PointNet1(nn.Module):
         if N % 128:
             raise ValueError("number of points must be a multiple of 128 (the flattened range image)")
         pts = L.f32c(x)
-        params = [(w.to(pts.device), b.to(pts.device)) for w, b in self._folded()]
+        # BatchNorm folding is redone only when a parameter / buffer changed (in-place edits bump ._version)
+        key = (tuple((id(t), t._version) for t in list(self.parameters()) + list(self.buffers())), pts.device)
+        if self._cache is None or self._cache[0] != key:
+            self._cache = (key, [(w.to(pts.device), b.to(pts.device)) for w, b in self._folded()], {})
+        params, scratches = self._cache[1], self._cache[2]
         st = L.R2dmPointNetWeights()
         for i, (w, b) in enumerate(params):
             st.weight[i] = w.data_ptr()
@@ -112,7 +122,10 @@ class PointNet1(nn.Module):
         out = torch.empty(B, 1024 + 512 + 256 + self.k, device=pts.device, dtype=torch.float32)
         with torch.cuda.device(pts.device):
             n = L.lib().r2dm_pointnet_scratch_bytes(dt, B, N)
-            scratch = torch.empty(n, dtype=torch.uint8, device=pts.device)
+            scratch = scratches.get((dt, B, N))
+            if scratch is None:
+                scratches.clear()
+                scratch = scratches[(dt, B, N)] = torch.empty(n, dtype=torch.uint8, device=pts.device)
             L.check(L.lib().r2dm_pointnet_features(dt, L.ptr(pts), C.byref(st), L.ptr(out), B, N, L.ptr(scratch), n,
                                                    L.stream_ptr()), "r2dm_pointnet_features")
         return out
