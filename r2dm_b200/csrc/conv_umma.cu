@@ -70,7 +70,9 @@ struct ConvTraits {
 };
 
 // silu(t) = h + h tanh(h) with h = t/2 (the 1/2 is folded into the affine coefficients): one MUFU op
-template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW>
+// PW: point-wise MLP extras of the 1x1 kernel (ReLU, per-channel maximum over pixels; pointnet.cu) - a separate
+// instantiation so that the network's own kernels keep their register allocation
+template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW, bool PW>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvParams p) {
   using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
@@ -553,8 +555,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int u = 0; u < NSUB; ++u) { s1p[u] = pack2(0.f, 0.f); s2p[u] = pack2(0.f, 0.f); }
         const f32x2 scale2 = pack2(p.scale, p.scale);
         // 1x1 launches: per-channel maximum over this thread's pixels (point-wise MLP + global max pool)
-        float cm[TAPS == 1 ? CB : 1];
-        if constexpr (TAPS == 1) {
+        float cm[PW ? CB : 1];
+        if constexpr (PW) {
 #pragma unroll
           for (int i = 0; i < CB; ++i) cm[i] = -INFINITY;
         }
@@ -606,8 +608,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll
                   for (int i = 0; i < PPU; ++i) o2[i] = fma2(r2[i], scale2, o2[i]);
                 }
-                if constexpr (TAPS == 1) {
-                  if (p.relu | (p.colmax != nullptr)) {
+                if constexpr (PW) {
+                  {
 #pragma unroll
                     for (int i = 0; i < PPU; ++i) {
                       float lo, hi;
@@ -624,7 +626,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                   s1p[sub] = add2(s1p[sub], o2[i]);
                   s2p[sub] = fma2(o2[i], o2[i], s2p[sub]);
                 }
-                if constexpr (TAPS == 1) {
+                if constexpr (PW) {
                   if (out == nullptr) continue;      // max-pool only: the tensor itself is not needed
                 }
                 uint4 pk = Elem<T>::pack2x(o2);
@@ -640,7 +642,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
             }
           }
         }
-        if constexpr (TAPS == 1 && !NCHW) {
+        if constexpr (PW && !NCHW) {
           if (p.colmax != nullptr) {
             // transposing butterfly: afterwards lane i holds the warp maximum of channel c0 + i (CB = 32) -
             // 31 shuffles instead of 5 per channel
@@ -847,10 +849,10 @@ int conv_trace_cap() { return g_trace_cap; }
 constexpr int kSmemBudget = 224 * 1024;     // dynamic smem per CTA (227 KB limit minus < 3 KB static)
 constexpr int kWresMaxBytes = 80 * 1024;    // keep the filter bank resident below this size
 
-template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW = false>
+template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW = false, bool PW = false>
 static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
-  auto kern = conv_umma_kernel<T, NT, HT, TAPS, KS, NCHW>;
+  auto kern = conv_umma_kernel<T, NT, HT, TAPS, KS, NCHW, PW>;
   if ((l.out_nchw != nullptr) != NCHW) return cudaErrorInvalidConfiguration;
   static unsigned long long configured = 0;   // one bit per device (the attribute is per device)
   if (first_use_on_this_device(configured)) {
@@ -909,7 +911,7 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.reverse = l.reverse;
   p.round_out = l.round_out;
   p.relu = l.relu; p.colmax = l.colmax;
-  if ((l.relu || l.colmax) && TAPS != 1) return cudaErrorInvalidConfiguration;
+  if ((l.relu || l.colmax != nullptr) != PW) return cudaErrorInvalidConfiguration;
   p.ktime = l.ktime;
   const int avail = kSmemBudget - 256 - p.coef_bytes - (p.wres ? static_cast<int>(wbytes) : 0);
   int stages = avail / p.stage_bytes;
@@ -963,6 +965,11 @@ static cudaError_t dispatch(const ConvLaunch& l, cudaStream_t s) {
     if (l.nt == 128 && l.ht == 1) return launch_one<T, 128, 1, 9, 1>(l, s);
     if (l.nt == 16 && l.ht == 4)
       return l.out_nchw ? launch_one<T, 16, 4, 9, 1, true>(l, s) : launch_one<T, 16, 4, 9, 1>(l, s);
+  } else if (l.taps == 1 && (l.relu || l.colmax != nullptr)) {
+    if (l.nt == 64 && l.ht == 2) return launch_one<T, 64, 2, 1, 4, false, true>(l, s);
+    if (l.nt == 128 && l.ht == 2) return launch_one<T, 128, 2, 1, 4, false, true>(l, s);
+    if (l.nt == 128 && l.ht == 1) return launch_one<T, 128, 1, 1, 4, false, true>(l, s);
+    if (l.nt == 64 && l.ht == 1) return launch_one<T, 64, 1, 1, 4, false, true>(l, s);
   } else if (l.taps == 1) {
     if (l.nt == 64 && l.ht == 2) return launch_one<T, 64, 2, 1, 4>(l, s);
     if (l.nt == 128 && l.ht == 2) return launch_one<T, 128, 2, 1, 4>(l, s);
