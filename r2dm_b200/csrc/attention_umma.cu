@@ -39,7 +39,12 @@ struct AttnParams {
 template <typename T, int HD>
 struct AttnTraits {
   static constexpr int CW = Elem<T>::CW;
-  static constexpr int KT = sizeof(T) == 2 ? 128 : 64;   // keys per tile
+  // (developer A/B: -DR2DM_ATTN_KT_BF16=64 gives 64-key tiles and three CTAs per SM for bf16 - measured slower,
+  //  0.106-0.110 vs 0.097 ms for the two launches of a forward)
+#ifndef R2DM_ATTN_KT_BF16
+#define R2DM_ATTN_KT_BF16 128
+#endif
+  static constexpr int KT = sizeof(T) == 2 ? R2DM_ATTN_KT_BF16 : 64;   // keys per tile
   static constexpr int KSTEP = 32 / sizeof(T);           // K extent of one MMA (16 bf16 / 8 tf32) = two 16-byte units
   static constexpr int PLANES = HD / CW;                 // 16-byte units per token per head
   static constexpr int PLANE_BYTES = 128 * 16;           // Q / P planes: 128 queries
@@ -55,7 +60,10 @@ struct AttnTraits {
 };
 
 template <typename T, int HD>
-__global__ void __launch_bounds__(128, 2) attention_umma_kernel(const __grid_constant__ AttnParams p) {
+#ifndef R2DM_ATTN_MINB
+#define R2DM_ATTN_MINB 2
+#endif
+__global__ void __launch_bounds__(128, R2DM_ATTN_MINB) attention_umma_kernel(const __grid_constant__ AttnParams p) {
   using Tr = AttnTraits<T, HD>;
   constexpr int CW = Tr::CW, KT = Tr::KT, PLANES = Tr::PLANES;
   constexpr int PLANE_BYTES = Tr::PLANE_BYTES, KV_PLANE_BYTES = Tr::KV_PLANE_BYTES;
@@ -261,7 +269,7 @@ static cudaError_t launch_attn(const PT& qkv, const PT& out, int heads, const CU
   return launch_pdl(kern, grid, dim3(128), Tr::SMEM, s, p);
 }
 
-int attention_key_tile(int dtype) { return dtype == kBF16 ? 128 : 64; }
+int attention_key_tile(int dtype) { return dtype == kBF16 ? R2DM_ATTN_KT_BF16 : 64; }
 
 cudaError_t attention_umma_launch(int dtype, PT qkv, PT out, int heads, const CUtensorMap& tm_q,
                                   const CUtensorMap& tm_kv, cudaStream_t s) {
