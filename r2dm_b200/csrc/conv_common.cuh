@@ -65,6 +65,7 @@ struct ConvParams {
   int coef_ch, coef_bytes;        // transform coefficient table at the start of dynamic smem: 2 x coef_ch floats
   int reverse;                    // walk the tiles back to front
   int round_out;                  // fp32: round the stored output to nearest tf32
+  int prefetch_w;                 // request the first ring fill's weights before griddepcontrol.wait
   int relu;                       // 1x1 only: max(0, .) after bias / scale
   float* colmax;                  // 1x1 only: [B][cout_pad] running maximum over pixels, or null
   int debug;  // developer ablation knob (R2DM_CONV_DEBUG): 1 no epilogue stores, 2 no MMA issue, 4 no TMA

@@ -69,6 +69,8 @@ struct ConvTraits {
                 "skip stage does not fit in a ring slot");
 };
 
+__device__ __forceinline__ bool get_prefetch(const ConvParams& p) { return p.prefetch_w != 0; }
+
 // silu(t) = h + h tanh(h) with h = t/2 (the 1/2 is folded into the affine coefficients): one MUFU op
 // PW: point-wise MLP extras of the 1x1 kernel (ReLU, per-channel maximum over pixels; pointnet.cu) - a separate
 // instantiation so that the network's own kernels keep their register allocation
@@ -141,6 +143,21 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES,
                     &wres_bar);
       }
+      // (option prefetch_w, measured +-0) Streamed weights do not depend on the previous kernel either: the weight part of the first ring fill is
+      // requested before the dependency wait (a CTA becomes resident as soon as its SM is free and then sits in
+      // griddepcontrol.wait until the slowest CTA of the previous launch has finished), so that only the activation
+      // boxes are left to fetch once the wait returns.  A complete_tx that lands before the matching
+      // arrive.expect_tx is fine: the phase cannot complete while the arrival is pending.
+      uint32_t pre = 0;
+      if (!p.wres && t_begin < t_end && get_prefetch(p)) {
+        int b, yt, xt, nt;
+        decode(t_begin, b, yt, xt, nt);
+        const uint8_t* wsrc = static_cast<const uint8_t*>(p.wpacked) + static_cast<size_t>(nt) * p.nk * Tr::B_BYTES;
+        pre = static_cast<uint32_t>(p.stages < p.nk ? p.stages : p.nk);
+        for (uint32_t ks = 0; ks < pre; ++ks)
+          bulk_load(smem_ring + static_cast<size_t>(ks) * p.stage_bytes + Tr::A_BYTES_AL,
+                    wsrc + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES, &full_bar[ks]);
+      }
       pdl_wait();
       uint32_t it = 0, ph = 0;
       int st = 0;   // ring slot / phase advance incrementally (no division per stage)
@@ -160,7 +177,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           // coordinates: (8-byte element within the padded row, half, row, plane, image)
           if (TAPS == 9) tma_load_5d(sa, tm, &full_bar[st], 2 * x0, 0, y0 - 1, plane0, b);
           else tma_load_5d(sa, tm, &full_bar[st], 2 * (x0 + 1), 0, y0, plane0, b);
-          if (!p.wres)
+          if (!p.wres && it >= pre)
             bulk_load(sa + Tr::A_BYTES_AL, wsrc + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES, &full_bar[st]);
           R2DM_TRACE(0, it);
         }
@@ -911,6 +928,7 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.reverse = l.reverse;
   p.round_out = l.round_out;
   p.relu = l.relu; p.colmax = l.colmax;
+  p.prefetch_w = get_option("prefetch_w", 0);   // experiment: +-0 (2.375 vs 2.376 ms per forward), off by default
   if ((l.relu || l.colmax != nullptr) != PW) return cudaErrorInvalidConfiguration;
   p.ktime = l.ktime;
   const int avail = kSmemBudget - 256 - p.coef_bytes - (p.wres ? static_cast<int>(wbytes) : 0);

@@ -114,7 +114,7 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
 namespace r2dm {
 // Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
 static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
-static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid"};
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid", "prefetch_w"};
 int get_option(const char* name, int dflt) {
   auto& m = option_map();
   auto it = m.find(name);
