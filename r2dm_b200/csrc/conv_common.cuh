@@ -40,6 +40,8 @@ struct XformParams {
   int debug;   // developer knob (R2DM_XF_DEBUG): 1 = skip transform math+copy, 2 = copy only
 };
 
+constexpr int kMaxPwChannels = 1024;   // widest point-wise layer with a fused max pool (PointNet: 1024)
+
 struct ConvParams {
   CUtensorMap tmap0, tmap1;
   CUtensorMap tmap2, tmap3;   // skip stages (folded 1x1 projection): raw skip input(s)

@@ -87,6 +87,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
   __shared__ float stat_w[2][8][NT / 8 > 0 ? NT / 8 : 1][2];   // [tile parity][epilogue warp][8-channel sub-chunk][sum, sumsq]
   __shared__ float grp_s[2][kNU];
   __shared__ __align__(16) float bias_s[NT];
+  // PW: running per-channel maximum of the image this CTA currently works on (all N tiles), flushed to global
+  // memory with one atomic per channel when the image changes - not one per tile
+  __shared__ float pw_max[PW ? kMaxPwChannels : 1];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.ktime != nullptr && threadIdx.x == 0) atomicMin(p.ktime, gtime());
@@ -529,9 +532,28 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
     const int ethread = threadIdx.x - kEpiWarp0 * 32;
     pdl_wait();
     int j = 0, cur_nt = -1;
+    int pw_b = -1;
+    auto pw_flush = [&](int bb) {     // all 256 epilogue threads
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = ethread; i < p.cout_pad; i += 256) {
+        const float v = pw_max[i];
+        if (bb >= 0 && v > -INFINITY) {
+          float* dst = p.colmax + static_cast<size_t>(bb) * p.cout_pad + i;
+          // float maximum with integer atomics: non-negative values order like ints, negative ones like
+          // reversed unsigned ints; the buffer starts at -inf
+          if (v >= 0.f) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(v));
+          else atomicMin(reinterpret_cast<unsigned int*>(dst), __float_as_uint(v));
+        }
+        pw_max[i] = -INFINITY;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
     for (int t = t_begin; t < t_end; ++t, ++j) {
       int b, yt, xt, nt;
       decode(t, b, yt, xt, nt);
+      if constexpr (PW) {
+        if (p.colmax != nullptr && b != pw_b) { pw_flush(pw_b); pw_b = b; }
+      }
       const int n0 = nt * NT, x = xt * 128 + m, y0 = yt * HT;
       const int buf = j & 1, par = j & 1;
       // the thread that holds pixel 0 (W-1) also writes the wrap halo column xp = W+1 (xp = 0): one predicated
@@ -675,10 +697,8 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                 cm[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
               }
             }
-            float* dst = p.colmax + static_cast<size_t>(b) * p.cout_pad + n0 + c0 + lane;
+            float* dst = pw_max + n0 + c0 + lane;      // shared-memory atomics: eight warps share a channel
             const float v = cm[0];
-            // float maximum with integer atomics: non-negative values order like ints, negative ones like
-            // reversed unsigned ints; the buffer starts at -inf
             if (v >= 0.f) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(v));
             else atomicMin(reinterpret_cast<unsigned int*>(dst), __float_as_uint(v));
           }
@@ -744,6 +764,9 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           p.stats[((static_cast<size_t>(b) * kNU + unit) * p.slots + slot) * 2 + k] = tot;
         }
       }
+    }
+    if constexpr (PW) {
+      if (p.colmax != nullptr) pw_flush(pw_b);
     }
   }
   tc_fence_before();
@@ -870,10 +893,11 @@ template <typename T, int NT, int HT, int TAPS, int KS, bool NCHW = false, bool 
 static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   using Tr = ConvTraits<T, NT, HT, TAPS, KS>;
   auto kern = conv_umma_kernel<T, NT, HT, TAPS, KS, NCHW, PW>;
+  constexpr int kBudget = kSmemBudget - (PW ? kMaxPwChannels * static_cast<int>(sizeof(float)) : 0);   // PW: static pw_max
   if ((l.out_nchw != nullptr) != NCHW) return cudaErrorInvalidConfiguration;
   static unsigned long long configured = 0;   // one bit per device (the attribute is per device)
   if (first_use_on_this_device(configured)) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBudget);
     if (e != cudaSuccess) return e;
   }
   ConvParams p;
@@ -930,8 +954,9 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.relu = l.relu; p.colmax = l.colmax;
   p.prefetch_w = get_option("prefetch_w", 0);   // experiment: +-0 (2.375 vs 2.376 ms per forward), off by default
   if ((l.relu || l.colmax != nullptr) != PW) return cudaErrorInvalidConfiguration;
+  if (PW && l.cout_pad > kMaxPwChannels) return cudaErrorInvalidValue;
   p.ktime = l.ktime;
-  const int avail = kSmemBudget - 256 - p.coef_bytes - (p.wres ? static_cast<int>(wbytes) : 0);
+  const int avail = kBudget - 256 - p.coef_bytes - (p.wres ? static_cast<int>(wbytes) : 0);
   int stages = avail / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   { const int cap = get_option("max_stages", kMaxStages); if (stages > cap) stages = cap; }
