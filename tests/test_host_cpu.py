@@ -44,7 +44,8 @@ def test_create_rejects_unsupported_configs_without_gpu():
     assert _lib.lib().r2dm_weight_arena_bytes(h) > 31_000_000 * 2
     ws1 = _lib.lib().r2dm_workspace_bytes(h, 1)
     ws8 = _lib.lib().r2dm_workspace_bytes(h, 8)
-    assert 0 < ws1 < ws8 < 8 * ws1 + (8 << 20)      # linear in the batch up to buffer-recycling slack
+    assert 0 < ws1 < ws8 < 8 * ws1 * 1.02 + (8 << 20)      # linear in the batch up to buffer-recycling slack
+    # (buffers are recycled by exact size: at B=1 one more pair of sizes coincides than at B>=2, 125.9 vs 127.5 MB per image)
     _lib.lib().r2dm_destroy(h)
 
 
