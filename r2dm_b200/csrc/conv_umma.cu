@@ -30,45 +30,6 @@
 
 namespace r2dm {
 
-template <typename T, int NT, int HT, int TAPS, int KS>
-struct ConvTraits {
-  static constexpr int CW = Elem<T>::CW;
-  static constexpr int KCH = KS * 2 * CW;
-  static constexpr int PLANES = 2 * KS;
-  static constexpr int AROWS = TAPS == 9 ? HT + 2 : HT;
-  static constexpr int APITCH = TAPS == 9 ? 130 : 128;
-  static constexpr int A_PLANE_BYTES = AROWS * APITCH * 16;
-  static constexpr int A_BYTES = PLANES * A_PLANE_BYTES;
-  static constexpr int A_BYTES_AL = (A_BYTES + 127) / 128 * 128;
-  // FUSE (3x3, NT = 64 and NT = 16 (N = 48); NT = 128 fuses two taps, N = 256): the vertical taps of one horizontal offset
-  // are ONE MMA with N = 192:
-  // the shifted A view of input row i feeds output rows i-1, i, i+1 (adjacent accumulator column
-  // blocks), because a 128x64x16 MMA cannot go below ~60 cycles (53 % of the tensor pipe, measured
-  // with tools/probe_mma_rate.cu) while N >= 128 runs at full rate.  Weights are then packed as
-  // [kx][plane][ky descending][co] so that any contiguous ky range is a contiguous row range of B.
-  static constexpr bool FUSE = (TAPS == 9 && (NT == 64 || NT == 16 || (NT == 128 && HT <= 2)));
-  static constexpr int B_PLANE_BYTES = (FUSE ? 3 : 1) * NT * 16;
-  static constexpr int B_TAP_BYTES = PLANES * B_PLANE_BYTES;          // one tap (or one kx block)
-  static constexpr int B_BYTES = (FUSE ? 3 : TAPS) * B_TAP_BYTES;
-  static constexpr int ACC_COLS = HT * NT;
-  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
-                                   : 2 * ACC_COLS <= 256 ? 256 : 512;
-  static_assert(2 * ACC_COLS <= 512, "double-buffered accumulators exceed TMEM");
-  static_assert(B_BYTES % 128 == 0, "weight stage must stay 128B aligned");
-  // Skip stages (3x3 kernels only): extra K stages of a 1x1 convolution over a second, untransformed input
-  // accumulated into the same tile - the ResidualBlock's skip projection (efficient_unet.py:87-91,108) folded into
-  // conv2.  One skip stage = SK_PLANES channel planes of the HT x 128 centre pixels + the matching weight rows;
-  // it reuses a ring slot, so it must fit in the 3x3 stage (resident 3x3 weights: the A part alone).
-  static constexpr int SK_PLANES = NT >= 128 ? 8 : 2;
-  static constexpr int SK_KCH = SK_PLANES * CW;
-  static constexpr int SK_A_PLANE_BYTES = HT * 128 * 16;
-  static constexpr int SK_A_BYTES = SK_PLANES * SK_A_PLANE_BYTES;
-  static constexpr int SK_B_PLANE_BYTES = NT * 16;
-  static constexpr int SK_B_BYTES = SK_PLANES * SK_B_PLANE_BYTES;
-  static_assert(TAPS != 9 || NT < 64 || SK_A_BYTES + SK_B_BYTES <= A_BYTES_AL + (NT >= 128 ? B_BYTES : 0),
-                "skip stage does not fit in a ring slot");
-};
-
 __device__ __forceinline__ bool get_prefetch(const ConvParams& p) { return p.prefetch_w != 0; }
 
 // silu(t) = h + h tanh(h) with h = t/2 (the 1/2 is folded into the affine coefficients): one MUFU op

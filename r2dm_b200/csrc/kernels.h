@@ -85,6 +85,11 @@ int conv_skip_planes(int nt);                  // channel planes per skip stage 
 size_t conv_packed_weight_bytes(int dtype, int taps, int nt, int cin_pad, int cout_pad);
 int conv_stat_slots(const ConvLaunch& l);
 cudaError_t conv_launch(const ConvLaunch& l, cudaStream_t s);
+// Several consecutive 3x3 convolutions of one resolution level in ONE persistent launch (conv_chain.cu): same tile
+// geometry, fused GroupNorm on every layer.  done: [n][B] ints of scratch; batch_split: images in the first group.
+constexpr int kMaxChainLayers = 6;
+bool conv_chain_supported(const ConvLaunch& l);
+cudaError_t conv_chain_launch(const ConvLaunch* const* ls, int n, int* done, int batch_split, cudaStream_t s);
 // Launch with programmatic dependent launch (PDL) allowed: the kernel may become resident while its stream
 // predecessor drains; it must execute griddepcontrol.wait (pdl_wait) before touching anything a predecessor
 // wrote or still reads.  All kernels of the sampling loop use it, so a CUDA graph of the loop has

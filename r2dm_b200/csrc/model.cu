@@ -67,6 +67,8 @@ struct Op {
   bool xf_film = false;   // conv with fused AdaGN: film pointers patched per forward
   CUtensorMap attn_tmap, attn_tmap_kv;  // ATTN: TMA maps of the packed qkv tensor (Q tile / K, V tiles)
   bool attn_exact = false;              // fp32 engine with option attn_exact: FMA-pipe kernel instead of kind::tf32
+  int chain_len = 0;                    // CONV: > 0 = this op and the next chain_len - 1 ops run as ONE conv_chain launch
+  int* chain_done = nullptr;            //       its [chain_len][B] tile counters (workspace tail)
 };
 
 }  // namespace
@@ -114,7 +116,7 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
 namespace r2dm {
 // Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
 static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
-static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid", "prefetch_w"};
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid", "prefetch_w", "chain", "chain_mask", "chain_nosplit", "chain_noclamp", "chain_rot"};
 int get_option(const char* name, int dflt) {
   auto& m = option_map();
   auto it = m.find(name);
@@ -451,6 +453,8 @@ struct Builder {
   }
 };
 
+constexpr size_t kChainCounterBytes = 64 * 1024;   // tile counters of the conv chains, after the planned buffers
+
 int validate_config(const r2dm_config& c) {
   if (c.gn_num_groups != kNU) return fail(-1, "gn_num_groups must be %d", kNU);
   if (c.base_channels % 64 != 0) return fail(-1, "base_channels must be a multiple of 64");
@@ -625,7 +629,7 @@ size_t r2dm_workspace_bytes(r2dm_handle h, int batch) {
   b.m = h;
   b.pl.m = h; b.pl.base = nullptr; b.pl.B = batch;
   b.build();
-  return b.pl.top + 4096;
+  return b.pl.top + 4096 + kChainCounterBytes;
 }
 
 int r2dm_bind_workspace(r2dm_handle h, void* workspace, size_t bytes, int batch, void* stream) {
@@ -670,6 +674,42 @@ int r2dm_bind_workspace(r2dm_handle h, void* workspace, size_t bytes, int batch,
       op.gn.beta = h->raw_ptr(op.gn_gamma + 1);
     }
     ++launches;
+  }
+  // Chains (option chain = 1, off by default): maximal runs of consecutive 3x3 convolutions with the same tile
+  // geometry (the ResidualBlock convs of one resolution level) become ONE persistent launch each (conv_chain.cu).
+  // Bit-identical results; measured +-0 on the forward, so the product keeps one launch per layer.
+  if (get_option("chain", 0)) {
+    size_t ctr_off = align_up(b.pl.top, 256);
+    const int n_ops = static_cast<int>(h->prog.size());
+    int n_chains = 0;
+    for (int i = 0; i < n_ops;) {
+      Op& first = h->prog[i];
+      int len = 0;
+      if (first.kind == Op::CONV && conv_chain_supported(first.conv)) {
+        len = 1;
+        while (i + len < n_ops && len < kMaxChainLayers) {
+          const Op& o = h->prog[i + len];
+          if (o.kind != Op::CONV || !conv_chain_supported(o.conv) || o.conv.nt != first.conv.nt ||
+              o.conv.ht != first.conv.ht || o.conv.out.H != first.conv.out.H || o.conv.out.W != first.conv.out.W ||
+              o.conv.cout_pad != first.conv.cout_pad || o.conv.cout != first.conv.cout)
+            break;
+          ++len;
+        }
+      }
+      if (len >= 2) {
+        const size_t need = static_cast<size_t>(len) * batch * sizeof(int);
+        const bool enabled = (get_option("chain_mask", -1) >> n_chains++) & 1;   // developer: pick chains by order
+        if (enabled && ctr_off + need <= bytes) {
+          first.chain_len = len;
+          first.chain_done = reinterpret_cast<int*>(h->ws + ctr_off);
+          ctr_off += align_up(need, 256);
+          launches -= len - 1;
+        }
+        i += len;
+      } else {
+        ++i;
+      }
+    }
   }
   h->n_launches = launches;
   // constant planes of the input staging tensor (coordinate encoding + zero padding)
@@ -738,14 +778,41 @@ static int launch_op(r2dm_handle h, Op& op, const float* x, const float* film, c
   return 0;
 }
 
+// Launches op i - or, when it starts a chain, the whole chain - and reports how many program entries that covered.
+static int launch_at(r2dm_handle h, int i, const float* x, const float* film, const int* step_ptr, int rows_per_step,
+                     int row_batch_stride, float* pred, cudaStream_t s, int* consumed) {
+  Op& op = h->prog[i];
+  *consumed = 1;
+  if (op.kind != Op::CONV || op.chain_len < 2)
+    return launch_op(h, op, x, film, step_ptr, rows_per_step, row_batch_stride, pred, s);
+  const ConvLaunch* ls[kMaxChainLayers];
+  for (int k = 0; k < op.chain_len; ++k) {
+    Op& o = h->prog[i + k];
+    if (o.xf_film) {
+      o.conv.xf.film = film; o.conv.xf.step_ptr = step_ptr;
+      o.conv.xf.rows_per_step = rows_per_step; o.conv.xf.row_batch_stride = row_batch_stride;
+    }
+    ls[k] = &o.conv;
+  }
+  // two image groups keep every CTA busy across layer boundaries; a single image has nothing to interleave with
+  const int B = op.conv.out.B;
+  const int split = (B >= 2 && !get_option("chain_nosplit", 0)) ? (B + 1) / 2 : B;
+  CUDA_TRY(conv_chain_launch(ls, op.chain_len, op.chain_done, split, s));
+  *consumed = op.chain_len;
+  return 0;
+}
+
 int r2dm_unet_forward(r2dm_handle h, const float* x, const float* film, const int* step_ptr, int rows_per_step,
                       int row_batch_stride, float* pred, void* stream) {
   if (!h || !x || !film || !pred) return fail(-1, "null argument");
   if (!h->ws) return fail(-1, "bind a workspace first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  for (Op& op : h->prog) {
-    int rc = launch_op(h, op, x, film, step_ptr, rows_per_step, row_batch_stride, pred, s);
+  const int n = static_cast<int>(h->prog.size());
+  for (int i = 0; i < n;) {
+    int used = 1;
+    int rc = launch_at(h, i, x, film, step_ptr, rows_per_step, row_batch_stride, pred, s, &used);
     if (rc) return rc;
+    i += used;
   }
   return 0;
 }
@@ -759,7 +826,9 @@ int r2dm_debug_forward_kinds(r2dm_handle h, const float* x, const float* film, f
   if (!h || !x || !film || !pred) return fail(-1, "null argument");
   if (!h->ws) return fail(-1, "bind a workspace first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  for (Op& op : h->prog) {
+  const int n = static_cast<int>(h->prog.size());
+  for (int i = 0; i < n;) {
+    Op& op = h->prog[i];
     int k = 0;
     switch (op.kind) {
       case Op::PACK_INPUT: k = 0; break;
@@ -769,9 +838,12 @@ int r2dm_debug_forward_kinds(r2dm_handle h, const float* x, const float* film, f
       case Op::UP: k = 5; break;
       case Op::ATTN: k = 6; break;
     }
-    if (!(kind_mask >> k & 1u)) continue;
-    int rc = launch_op(h, op, x, film, nullptr, 0, 1, pred, s);
-    if (rc) return rc;
+    int used = (op.kind == Op::CONV && op.chain_len >= 2) ? op.chain_len : 1;
+    if (kind_mask >> k & 1u) {
+      int rc = launch_at(h, i, x, film, nullptr, 0, 1, pred, s, &used);
+      if (rc) return rc;
+    }
+    i += used;
   }
   return 0;
 }
@@ -789,11 +861,18 @@ int r2dm_profile_forward(r2dm_handle h, const float* x, const float* film, float
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
   const double es = dtype_size(h->dtype);
+  int covered = 0;   // program entries already executed by a chain launch (their time is booked on its first entry)
   for (int i = 0; i < n; ++i) {
     Op& op = h->prog[i];
     CUDA_TRY(cudaEventRecord(ev[i], s));
-    int rc = launch_op(h, op, x, film, nullptr, 0, 1, pred, s);
-    if (rc) return rc;
+    if (covered > 0) {
+      --covered;
+    } else {
+      int used = 1;
+      int rc = launch_at(h, i, x, film, nullptr, 0, 1, pred, s, &used);
+      if (rc) return rc;
+      covered = used - 1;
+    }
     double fl = 0, by = 0;
     int k = 0;
     auto tb = [&](const PT& t) { return static_cast<double>(t.B) * t.C * t.H * t.W * es; };

@@ -415,7 +415,7 @@ class UNetEngine:
             film = self.cond_embed(cond)
             pred = torch.empty_like(x)
             self.bind(x.shape[0])
-            cap = self.launches_per_forward
+            cap = 1024     # program entries (>= launches: a chain of convolutions is one launch, several entries)
             kind, ms = (C.c_int * cap)(), (C.c_float * cap)()
             fl, by = (C.c_double * cap)(), (C.c_double * cap)()
             n = L.check(self.lib.r2dm_profile_forward(self.h, L.ptr(x), L.ptr(film), L.ptr(pred), L.stream_ptr(),

@@ -116,3 +116,34 @@ def test_errors():
         cpu.model(torch.randn(1, 2, 64, 1024), torch.zeros(1))
     with pytest.raises(NotImplementedError):
         ddpm(torch.randn(1, 2, 16, 1024).cuda())
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_conv_chain_option_is_bit_identical(precision):
+    """Option `chain` (off by default): the ResidualBlock convolutions of a resolution level run as ONE persistent
+    launch with per-(layer, image) dependency counters (csrc/conv_chain.cu).  Same tiles, same MMA order, same
+    epilogue arithmetic: the outputs must be bit-identical to the one-launch-per-layer path, for an odd batch
+    (unequal image groups), a single image (one group) and the benchmarked shape."""
+    from r2dm_b200 import _lib as L
+    from tests.helpers import H_CFG
+    cases = [(SMALL_CFG, 3), (SMALL_CFG, 1), (H_CFG, 8)] if precision == "bf16" else [(SMALL_CFG, 2)]
+    for cfg, B in cases:
+        sd = O.random_state_dict(cfg, 21)
+        g = torch.Generator().manual_seed(4)
+        x = torch.randn(B, 2, *cfg.resolution, generator=g).cuda()
+        cond = torch.linspace(-5.0, 5.0, B).cuda()
+        outs, launches = [], []
+        for chain in (0, 1):
+            L.check(L.lib().r2dm_set_option(b"chain", chain))
+            try:
+                ddpm = make_ddpm(cfg, sd, precision=precision)      # the option is read when the workspace is planned
+                y = ddpm.model(x, cond)
+                y2 = ddpm.model(x, cond)                               # counters are re-armed on every launch
+                torch.cuda.synchronize()
+                assert torch.equal(y, y2)
+                outs.append(y.clone())
+                launches.append(ddpm.model.engine(precision).launches_per_forward)
+            finally:
+                L.check(L.lib().r2dm_set_option(b"chain", 0))
+        assert launches[1] < launches[0], launches
+        assert torch.equal(outs[0], outs[1]), f"chain launch changed the result ({cfg.resolution}, B={B})"

@@ -46,7 +46,7 @@ for _ in range(10):
     times.append(e0.elapsed_time(e1) / NF)
 # per-launch durations INSIDE a graph replay, recorded by the conv kernels themselves (globaltimer)
 from r2dm_b200 import _lib as L  # noqa: E402
-nl = eng.launches_per_forward
+nl = 256   # program entries (>= launches)
 kt = torch.zeros(nl, 2, dtype=torch.int64, device="cuda")
 L.check(L.lib().r2dm_debug_set_ktime(eng.h, L.ptr(kt)))
 g1 = torch.cuda.CUDAGraph()
