@@ -116,7 +116,7 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
 namespace r2dm {
 // Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
 static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
-static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid", "prefetch_w", "chain", "chain_mask", "chain_nosplit", "chain_noclamp", "chain_rot"};
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid", "prefetch_w", "chain", "chain_mask", "chain_nosplit", "chain_noclamp", "chain_rot", "unfuse_hw"};
 int get_option(const char* name, int dflt) {
   auto& m = option_map();
   auto it = m.find(name);
@@ -400,7 +400,17 @@ struct Builder {
         const std::string p = b.name + ".residual_blocks." + std::to_string(i);
         const int x0 = h, x1 = (i == 0) ? h2 : -1;
         // GroupNorm+SiLU and AdaGN+SiLU run inside the consumer convolutions (operand transform)
-        const int h1 = conv(p + ".conv1", x0, x1, -1, 1.f, true, false, 1, m->raw_by_name.at(p + ".norm1.weight"));
+        // experiment (option unfuse_hw, off): below this many pixels per image apply GroupNorm / AdaGN + SiLU ONCE in
+        // a stand-alone pass instead of once per N tile and halo row inside the conv (12x redundant at 8 x 128)
+        const bool unfuse = T(x0).H * T(x0).W <= get_option("unfuse_hw", 0);
+        int h1;
+        if (unfuse) {
+          const int n1 = gn(x0, x1, m->raw_by_name.at(p + ".norm1.weight"), "", true);
+          h1 = conv(p + ".conv1", n1, -1, -1, 1.f, true);
+          pl.release(n1);
+        } else {
+          h1 = conv(p + ".conv1", x0, x1, -1, 1.f, true, false, 1, m->raw_by_name.at(p + ".norm1.weight"));
+        }
         int res = x0, sk = -1;
         std::string fold;
         if (m->conv_by_name.count(p + ".skip")) {
@@ -412,7 +422,14 @@ struct Builder {
             res = sk;
           }
         }
-        const int o = conv(p + ".conv2", h1, -1, res, rs, true, false, 2, -1, p + ".norm2.proj.1", fold, x0, x1);
+        int o;
+        if (unfuse) {
+          const int n2 = gn(h1, -1, -1, p + ".norm2.proj.1", true);
+          o = conv(p + ".conv2", n2, -1, res, rs, true, false, 0, -1, "", fold, x0, x1);
+          pl.release(n2);
+        } else {
+          o = conv(p + ".conv2", h1, -1, res, rs, true, false, 2, -1, p + ".norm2.proj.1", fold, x0, x1);
+        }
         pl.release(h1);
         if (sk >= 0) pl.release(sk);
         pl.release(x0);
