@@ -229,3 +229,34 @@ def test_pointnet_features_gpu(fx, precision):
     # batch composition must not matter (per-cloud max pool, per-cloud transform)
     y2 = net(pn["small"][1:2].cuda()).cpu()
     assert torch.equal(y2[0], net(pn["small"].cuda()).cpu()[1])
+
+
+@pytest.mark.gpu
+def test_consumer_edge_cases_gpu():
+    """Degenerate inputs: points on the camera plane (z = 0: kornia's divide guard), at the origin (zero weight),
+    behind the camera, the smallest point image PointNet accepts, and shapes the C ABI must reject."""
+    from r2dm_b200 import pointnet as P
+    from r2dm_b200 import render as R
+    from r2dm_b200._lib import R2dmError
+    pts = torch.tensor([[[0.1, 0.2, 0.0], [0.0, 0.0, 0.0], [0.2, -0.1, 0.5], [0.3, 0.3, -0.7], [1e-9, 0.0, 1e-9]]])
+    y = R.render_point_clouds(pts.cuda(), size=64).cpu()
+    ref = RO.render_point_clouds(pts, size=64)
+    assert torch.isfinite(y).all() and rel_l2(y, ref) < 1e-5
+    # a single bin pair, every point on an edge or outside
+    pc = torch.tensor([[-5.0, 0.0, 0.0], [5.0, 5.0, 0.0], [0.0, -5.0, 3.0], [0.0, 0.0, 4.0], [6.0, 0.0, 0.0]])
+    kw = dict(field_size=10.0, bins=2, min_depth=1.0, max_depth=8.0)
+    assert torch.equal(R.point_cloud_to_histogram(pc.cuda(), **kw).cpu(), RO.point_cloud_to_histogram(pc, **kw))
+    # normals of a plane are constant; d larger than the image height clamps at the border rows
+    hh, ww = torch.meshgrid(torch.arange(8.0), torch.arange(256.0), indexing="ij")
+    plane = torch.stack([ww, hh, 0.5 * ww + 2.0 * hh])[None]
+    n = R.estimate_surface_normal(plane.cuda(), d=3, mode="mean").cpu()
+    assert rel_l2(n, RO.estimate_surface_normal(plane, d=3, mode="mean")) < 1e-5
+    # PointNet: 128 points is the smallest image; 100 is rejected before any launch
+    net = P.PointNet1(k=4).eval().cuda()
+    net.load_state_dict(RO.random_pointnet_state_dict(9, 4))
+    x = torch.randn(2, 3, 128, generator=torch.Generator().manual_seed(3))
+    assert rel_l2(net(x.cuda()), RO.pointnet_features(RO.random_pointnet_state_dict(9, 4), x)) < 3e-3
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 3, 100, device="cuda"))
+    with pytest.raises(R2dmError):
+        R.render_point_clouds(pts.cuda(), size=8192)          # accumulator index would leave fp32's exact range
