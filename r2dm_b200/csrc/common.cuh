@@ -97,6 +97,9 @@ __host__ __device__ __forceinline__ size_t pt_index(int b, int planes, int pl, i
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// for values that are rounded to tf32 (2^-11) right afterwards: approximate division (MUFU.RCP + FMUL, 2 ulp)
+// instead of the IEEE division sequence
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -381,7 +381,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
                 asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
                 v2[k] = fma2(t2, pack2(tl, th), t2);
               } else {
-                v2[k] = pack2(silu_f(lo), silu_f(hi));
+                v2[k] = pack2(silu_fast(lo), silu_fast(hi));
               }
             } else {
               v2[k] = t2;

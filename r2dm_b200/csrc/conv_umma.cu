@@ -424,7 +424,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
                   v2[k] = fma2(t2, pack2(tl, th), t2);      // h + h tanh(h), h = t / 2 (folded into a, d)
                 } else {
-                  v2[k] = pack2(silu_f(lo), silu_f(hi));
+                  v2[k] = pack2(silu_fast(lo), silu_fast(hi));
                 }
               } else {
                 v2[k] = t2;
