@@ -336,7 +336,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
           }
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        const float fold = (X.silu && sizeof(T) == 2) ? 0.5f : 1.f;
+        const float fold = X.silu ? 0.5f : 1.f;   // tanh-form SiLU for both engines (see conv_umma.cu)
 #pragma unroll
         for (int k = 0; k < CPT; ++k) {
           const int c = t256 + k * 256;
@@ -375,14 +375,10 @@ conv_chain_kernel(const __grid_constant__ ChainParams p) {
             if (X.silu) {
               float lo, hi;
               unpack2(t2, lo, hi);
-              if (sizeof(T) == 2) {
-                float tl, th;
-                asm("tanh.approx.f32 %0, %1;" : "=f"(tl) : "f"(lo));
-                asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
-                v2[k] = fma2(t2, pack2(tl, th), t2);
-              } else {
-                v2[k] = pack2(silu_fast(lo), silu_fast(hi));
-              }
+              float tl, th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(tl) : "f"(lo));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
+              v2[k] = fma2(t2, pack2(tl, th), t2);
             } else {
               v2[k] = t2;
             }

@@ -28,6 +28,13 @@
 // Elevation borders come from TMA out-of-bounds zero fill; the azimuth wrap from the halo columns.
 #include "conv_common.cuh"
 
+// SiLU in the operand transform: h + h tanh(h), h = t / 2, with tanh.approx (one MUFU, 2^-11 relative) for BOTH engines:
+// the result is rounded to bf16 (2^-9) or tf32 (2^-11) right after.  -DR2DM_F32_TANH=0 restores x / (1 + exp(-x)) in the
+// fp32 engine (measured: same trajectory errors, forward 2.72 vs 2.62 ms at B=4).
+#ifndef R2DM_F32_TANH
+#define R2DM_F32_TANH 1
+#endif
+
 namespace r2dm {
 
 __device__ __forceinline__ bool get_prefetch(const ConvParams& p) { return p.prefetch_w != 0; }
@@ -374,7 +381,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           }
           asm volatile("bar.sync 2, 256;" ::: "memory");
           // with the fast SiLU the coefficients produce h = t/2 directly
-          const float fold = (p.xf.silu && sizeof(T) == 2) ? 0.5f : 1.f;
+          const float fold = (p.xf.silu && (sizeof(T) == 2 || R2DM_F32_TANH)) ? 0.5f : 1.f;
 #pragma unroll
           for (int k = 0; k < CPT; ++k) {
             const int c = t256 + k * 256;
@@ -418,7 +425,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
               if (p.xf.silu) {
                 float lo, hi;
                 unpack2(t2, lo, hi);
-                if (sizeof(T) == 2) {
+                if (sizeof(T) == 2 || R2DM_F32_TANH) {
                   float tl, th;
                   asm("tanh.approx.f32 %0, %1;" : "=f"(tl) : "f"(lo));
                   asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hi));
