@@ -27,6 +27,14 @@
 
 namespace r2dm {
 
+// exp2 as ONE MUFU: exp2f() wraps it in a range fix-up for results below 2^-126 (FSETP + two predicated FMULs per
+// value, 3/4 of the softmax's exponential instructions); a probability that small is zero next to the row's 1.0
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnParams {
   CUtensorMap tmap;   // packed qkv, box = 128 px x (hd/CW) planes (Q tile)
   CUtensorMap tmap_kv;  // same tensor, box = KT px (K / V tiles)
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(128, R2DM_ATTN_MINB) attention_umma_kernel(con
       for (int i = 0; i < 32; ++i) tmax = fmaxf(tmax, s[i]);
     }
     const float m_new = fmaxf(m, tmax * p.scale_log2);
-    const float corr = exp2f(m - m_new);
+    const float corr = ex2_approx(m - m_new);
     float lsum = 0.f;
     // ---- pass 2: probabilities -> shared memory (A operand layout: [key chunk][query][8 keys])
 #pragma unroll
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(128, R2DM_ATTN_MINB) attention_umma_kernel(con
         float pv[CW];
 #pragma unroll
         for (int i = 0; i < CW; ++i) {
-          pv[i] = exp2f(fmaf(s[u * CW + i], p.scale_log2, -m_new));
+          pv[i] = ex2_approx(fmaf(s[u * CW + i], p.scale_log2, -m_new));
           lsum += pv[i];
         }
         *reinterpret_cast<uint4*>(sP + ((c0 / CW + u) * 128 + tid) * 16) = Elem<T>::pack_mma(pv);
