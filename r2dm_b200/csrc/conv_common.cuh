@@ -67,6 +67,7 @@ struct ConvParams {
   int coef_ch, coef_bytes;        // transform coefficient table at the start of dynamic smem: 2 x coef_ch floats
   int reverse;                    // walk the tiles back to front
   int round_out;                  // fp32: round the stored output to nearest tf32
+  int l2_hint;                    // experiment: activation loads with an L2 evict_first policy
   int prefetch_w;                 // request the first ring fill's weights before griddepcontrol.wait
   int relu;                       // 1x1 only: max(0, .) after bias / scale
   float* colmax;                  // 1x1 only: [B][cout_pad] running maximum over pixels, or null

@@ -130,6 +130,7 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
                     wsrc + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES, &full_bar[ks]);
       }
       pdl_wait();
+      const uint64_t l2pol = p.l2_hint ? l2_policy_evict_first() : 0ull;
       uint32_t it = 0, ph = 0;
       int st = 0;   // ring slot / phase advance incrementally (no division per stage)
       for (int t = t_begin; t < t_end; ++t) {
@@ -146,7 +147,12 @@ conv_umma_kernel(const __grid_constant__ ConvParams p) {
           const int plane0 = (second ? ks - p.ksplit : ks) * Tr::PLANES;
           const CUtensorMap* tm = second ? &p.tmap1 : &p.tmap0;
           // coordinates: (8-byte element within the padded row, half, row, plane, image)
-          if (TAPS == 9) tma_load_5d(sa, tm, &full_bar[st], 2 * x0, 0, y0 - 1, plane0, b);
+          if (p.l2_hint) {
+            // experiment (option l2_evict_first): activations are streamed once per launch - let them leave L2 first so
+            // that the output this launch writes is still resident when the next launch reads it
+            if (TAPS == 9) tma_load_5d_hint(sa, tm, &full_bar[st], 2 * x0, 0, y0 - 1, plane0, b, l2pol);
+            else tma_load_5d_hint(sa, tm, &full_bar[st], 2 * (x0 + 1), 0, y0, plane0, b, l2pol);
+          } else if (TAPS == 9) tma_load_5d(sa, tm, &full_bar[st], 2 * x0, 0, y0 - 1, plane0, b);
           else tma_load_5d(sa, tm, &full_bar[st], 2 * (x0 + 1), 0, y0, plane0, b);
           if (!p.wres && it >= pre)
             bulk_load(sa + Tr::A_BYTES_AL, wsrc + static_cast<size_t>(ks) * Tr::B_BYTES, Tr::B_BYTES, &full_bar[st]);
@@ -920,6 +926,7 @@ static cudaError_t launch_one(const ConvLaunch& l, cudaStream_t s) {
   p.reverse = l.reverse;
   p.round_out = l.round_out;
   p.relu = l.relu; p.colmax = l.colmax;
+  p.l2_hint = get_option("l2_evict_first", 0);
   p.prefetch_w = get_option("prefetch_w", 0);   // experiment: +-0 (2.375 vs 2.376 ms per forward), off by default
   if ((l.relu || l.colmax != nullptr) != PW) return cudaErrorInvalidConfiguration;
   if (PW && l.cout_pad > kMaxPwChannels) return cudaErrorInvalidValue;

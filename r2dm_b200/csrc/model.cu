@@ -116,7 +116,7 @@ int add_raw(r2dm_model* m, const std::string& name, size_t numel) {
 namespace r2dm {
 // Developer options: name -> value; the environment (R2DM_OPT_<NAME>, upper case) seeds a name on first use.
 static std::map<std::string, int>& option_map() { static std::map<std::string, int> m; return m; }
-static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid", "prefetch_w", "chain", "chain_mask", "chain_nosplit", "chain_noclamp", "chain_rot", "unfuse_hw"};
+static const char* const kOptionNames[] = {"serpentine", "ht1_max_tiles", "max_stages", "fold_skip", "attn_exact", "compact_grid", "prefetch_w", "chain", "chain_mask", "chain_nosplit", "chain_noclamp", "chain_rot", "unfuse_hw", "l2_evict_first"};
 int get_option(const char* name, int dflt) {
   auto& m = option_map();
   auto it = m.find(name);

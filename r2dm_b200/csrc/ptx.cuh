@@ -133,6 +133,22 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* desc, ui
         "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// The same with an L2 eviction-priority hint (createpolicy): `policy` from l2_policy_evict_first() / _last().
+__device__ __forceinline__ void tma_load_5d_hint(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3, int c4, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 // Plain (non-tensor) bulk copy global -> shared, completion on an mbarrier.
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes,
                                           uint64_t* bar) {
